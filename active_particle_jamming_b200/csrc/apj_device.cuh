@@ -1,0 +1,192 @@
+// Device-side data model shared by all kernels of the B200 hot path.
+//
+// HBM layout (all fp64, SoA, particles kept in CELL ORDER -- re-sorted at every Verlet rebuild;
+// cells are numbered cy + cx*b so one column of cells is one contiguous run of particles):
+//   XY[2]   {x, y}                  16 B, ping-pong by ctl.cur: a step reads half `cur` and
+//   CS[2]   {cos(phi), sin(phi)}    16 B  writes half `cur^1`
+//   XR[2]   x_real (unwrapped position), ping-pong with XY so a speculative step can be dropped
+//   RR, X0, XO, V, PHI, ID, BOX [2]  fields that only move at a rebuild; ping-pong by ctl.gen
+//           (RR = {R, 1/R}: Cell::R and Cell::Rinv, jamming.cpp:297-298)
+//   tiles   one TileDesc per work block: a run of <= ppb = tb/G consecutive particles of ONE cell
+//           column plus the <= 6 contiguous particle runs ("pieces") that hold every cell
+//           adjacent to the block's cells. The step kernel copies the pieces into shared
+//           memory with TMA bulk copies; all neighbour gathers then hit shared memory.
+//   list    full Verlet list in TILE-LOCAL 16-bit slots, two entries per 32-bit word, sorted by
+//           distance at build time; word w of particle p sits at [w / G][p * G + w % G] of the
+//           block's [round][tb threads] array, so each sweep round is one conflict-free row
+// One SysCtl per batched system (replica) holds geometry, parities, COM and the step counter;
+// kernels read it at entry, the last block of the step kernel commits to it.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+// Truncated literals are part of the reference algorithm (jamming.cpp:3-4).
+#define APJ_PI 3.14159265
+#define APJ_PI2 6.28318531
+
+#define APJ_TB_MAX 256      // largest thread block of the step kernel (particles per block = tb / G)
+#define APJ_MAX_PIECES 6
+
+struct __align__(64) TileDesc {
+    int g0;         // first particle (absolute index) of the block
+    int n;          // particles in the block (1..ppb)
+    int own_slot;   // tile slot of particle g0
+    int info;       // npieces | wraps << 8 | list words of the longest list << 16
+    int pstart[APJ_MAX_PIECES];  // absolute particle index where each piece starts
+    int plen[APJ_MAX_PIECES];    // particles in each piece (tile slots are the concatenation)
+};
+
+struct __align__(128) SysCtl {
+    // geometry (Engine::L, Lover2, lp, b, nbox; jamming.cpp:99-103)
+    double L, Lover2, lp;
+    int b, nbox;
+    int cell_base;  // offset of this system's cells in the global cell arrays (nbox+1 slots each)
+    int col_base;   // offset of this system's columns in the per-column scratch (b+1 slots each)
+    // activity (Engine::CFself / CTnoise) and the relax() ramp (jamming.cpp:516-520)
+    double CFself, CTnoise;
+    long long ramp_len, ramp_t0;
+    // dynamic state
+    int cur;         // parity of XY / CS / XR
+    int gen;         // parity of the rebuild-permuted arrays
+    int stale;       // 1: lists must be rebuilt before the next step can run
+    int save_old;    // 1: the pending rebuild was fired by the skin test (saveOldPositions + resetCounter++)
+    int no_self_once;  // drop the alignment self term for the next committed step
+    int list_max, overflow;
+    unsigned ticket;
+    int nblk;        // work blocks in use (<= DevState::maxblk)
+    int tile_max;    // largest tile (slots) of the current decomposition
+    long long step, target;
+    long long reset_counter, n_rebuilds, n_discarded;
+    double COM[2], COM_old[2], COM0[2];
+};
+
+struct DevState {
+    int n_sys, N;          // systems, particles per system
+    long long ntot;        // n_sys * N
+    int G;                 // lanes per particle in the sweep (1, 2, 4 or 8)
+    int tb;                // threads per work block of the step kernel (128 or 256)
+    int ppb;               // particles per work block = tb / G
+    int smem_rounds;       // list rows staged in shared memory (the rest, rare, is read from global)
+    int maxblk;            // work blocks reserved per system (N/ppb + b + 1)
+    int S;                 // list capacity per particle (even)
+    int max_rounds;        // ceil(S/2 / G): rows of the per-block list array
+    int tile_cap;          // shared-memory tile capacity in slots
+    double dt, rn2, rs2, skin;  // skin = rs - rn (jamming.cpp:611)
+    unsigned long long seed;
+    SysCtl* ctl;
+    double2* XY[2];
+    double2* CS[2];
+    double2* XR[2];
+    double2* RR[2];
+    double2* X0[2];
+    double2* XO[2];
+    double2* V[2];
+    double* PHI[2];
+    int* ID[2];
+    int* BOX[2];  // internal cell index cy + cx*b (columns contiguous)
+    TileDesc* tiles;      // n_sys * maxblk
+    unsigned* list32;     // n_sys * maxblk * max_rounds * tb
+    int* cnt;             // per particle
+    int* boxnew;
+    int* perm;
+    int* cell_count;   // zero between rebuilds
+    int* cell_start;   // per system nbox+1 entries, absolute particle indices
+    int* cell_cursor;
+    int* col_blk;      // per system b+1 entries: first work block of each column
+    double4* partials;  // per work block {sum x_real, sum y_real, top1 d2, top2 d2}
+    double4* gpartials; // per group of 32 work blocks
+    unsigned* gticket;  // per group arrival counter (zero between launches)
+    int maxgrp;         // groups reserved per system
+};
+
+// Engine::delta_norm (jamming.cpp:872-880) for |delta| < 1.5 L: one conditional add of -L or +L
+// gives the same value as the reference's while loop (k*L with k = +-1 is exact).
+__device__ __forceinline__ double apj_wrap1(double d, double L, double Lh) {
+    if (d < -Lh) d += L;
+    else if (d >= Lh) d -= L;
+    return d;
+}
+// General form (used where the argument is not bounded by the box).
+__device__ __forceinline__ double apj_delta_norm(double d, double L, double Lh) {
+    if (d < -Lh) { do { d += L; } while (d < -Lh || d >= Lh); }
+    else if (d >= Lh) { do { d -= L; } while (d < -Lh || d >= Lh); }
+    return d;
+}
+// dx*dx + dy*dy with the reference's rounding (two products, one sum; no FMA contraction), so
+// that distance predicates are bit-identical to the CPU build (SURVEY §7 "hard parts").
+__device__ __forceinline__ double apj_d2(double dx, double dy) {
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+
+// Philox4x32-10 (Salmon et al. SC'11). counter = (id, step_lo, step_hi, system), key = seed.
+__device__ __forceinline__ unsigned apj_philox_word0(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+                                                     unsigned k0, unsigned k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+// boost::uniform_real<>(-PI, PI) over a 32-bit engine (Boost 1.64 generate_uniform_real):
+// u / 2^32 * (PI - (-PI)) + (-PI)   
+__device__ __forceinline__ double apj_u32_to_randuni(unsigned u) {
+    return __dadd_rn(__dmul_rn(__dmul_rn((double)u, 1.0 / 4294967296.0), APJ_PI - (-APJ_PI)), -APJ_PI);
+}
+
+// top-2 merge of two (largest, second) pairs -- the multiset the reference's sequential scan
+// keeps (jamming.cpp:607-608).
+__device__ __forceinline__ void apj_top2_merge(double& a1, double& a2, double b1, double b2) {
+    if (b1 > a1) { a2 = fmax(a1, b2); a1 = b1; }
+    else { a2 = fmax(a2, b1); }
+}
+
+// tile slot of absolute particle index j (j must lie in one of the pieces)
+__device__ __forceinline__ int apj_slot_of(const TileDesc& d, int j) {
+    int off = 0;
+    const int npieces = d.info & 0xff;
+#pragma unroll
+    for (int p = 0; p < APJ_MAX_PIECES; p++) {
+        if (p < npieces) {
+            const int r = j - d.pstart[p];
+            if (r >= 0 && r < d.plen[p]) return off + r;
+            off += d.plen[p];
+        }
+    }
+    return -1;
+}
+
+// ---- TMA bulk copy (global -> shared) + mbarrier, sm_90+/sm_100a PTX ----------------------
+__device__ __forceinline__ unsigned apj_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void apj_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(apj_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void apj_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(apj_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void apj_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(apj_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(apj_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void apj_mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(apj_smem_addr(bar)), "r"(parity) : "memory");
+    }
+}
+
+// host-side launchers (one per .cu)
+struct ApjLaunch { cudaStream_t stream; long long* launch_counter; };
+void apj_launch_step(const DevState& st, const ApjLaunch& l, const double* noise_by_id, int always_full);
+void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nbox, int max_b);
+int apj_configure_kernels(const DevState& st);
+int apj_max_list_capacity();

@@ -1,0 +1,711 @@
+// Host side of the C ABI (include/apj_b200.h): owns device memory, the stream, the step graph
+// and the per-system control blocks. No physics runs on the host; the only host arithmetic is
+// setup that the reference also does once outside the hot loop (Rinv, cos/sin of the uploaded
+// phi, the initial COM sum in index order -- jamming.cpp:298, :332-333, :761-774).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/apj_b200.h"
+#include "apj_device.cuh"
+#include "apj_observe.cuh"
+
+static thread_local std::string g_create_error;
+
+struct apj_engine {
+    apj_config cfg{};
+    DevState st{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaGraphExec_t group_exec = nullptr;
+    int m = 16;                 // step launches per group
+    int kernels_per_group = 0;
+    int max_nbox = 0;
+    int max_b = 0;
+    long long total_cols = 0;   // sum of b+1
+    long long total_cells = 0;  // sum of nbox+1
+    long long launches = 0;
+    bool have_state = false;
+    std::vector<SysCtl> hctl;
+    std::vector<void*> allocs;
+    double* d_noise = nullptr;
+    ApjObsScratch obs{};
+    std::string err;
+};
+
+#define APJ_CUDA(e, call)                                                                   \
+    do {                                                                                    \
+        cudaError_t _s = (call);                                                            \
+        if (_s != cudaSuccess) {                                                            \
+            char _b[512];                                                                   \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_s), __FILE__, __LINE__); \
+            (e)->err = _b;                                                                  \
+            return APJ_E_CUDA;                                                              \
+        }                                                                                   \
+    } while (0)
+
+static int fail(apj_engine* e, int code, const std::string& msg) {
+    if (e) e->err = msg; else g_create_error = msg;
+    return code;
+}
+
+extern "C" const char* apj_version(void) { return "apj_b200 0.1 (sm_100a)"; }
+extern "C" const char* apj_last_error(const apj_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+template <class T>
+static int dev_alloc(apj_engine* e, T** p, size_t count) {
+    void* q = nullptr;
+    APJ_CUDA(e, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    APJ_CUDA(e, cudaMemsetAsync(q, 0, std::max<size_t>(count, 1) * sizeof(T), e->stream));
+    e->allocs.push_back(q);
+    *p = (T*)q;
+    return APJ_OK;
+}
+
+static int pull_ctl(apj_engine* e) {
+    APJ_CUDA(e, cudaMemcpyAsync(e->hctl.data(), e->st.ctl, sizeof(SysCtl) * e->hctl.size(), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    return APJ_OK;
+}
+static int push_ctl(apj_engine* e) {
+    APJ_CUDA(e, cudaMemcpyAsync(e->st.ctl, e->hctl.data(), sizeof(SysCtl) * e->hctl.size(), cudaMemcpyHostToDevice, e->stream));
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    return APJ_OK;
+}
+
+__global__ void apj_add_target_kernel(SysCtl* ctl, int n_sys, long long n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_sys) ctl[s].target = ctl[s].step + n;
+}
+
+static ApjLaunch launcher(apj_engine* e, bool count) { return ApjLaunch{e->stream, count ? &e->launches : nullptr}; }
+
+static int build_group_graph(apj_engine* e) {
+    if (e->group_exec) { cudaGraphExecDestroy(e->group_exec); e->group_exec = nullptr; }
+    if (e->cfg.flags & APJ_FLAG_NO_GRAPH) return APJ_OK;
+    cudaGraph_t graph = nullptr;
+    long long dummy = 0;
+    ApjLaunch l{e->stream, &dummy};
+    APJ_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    for (int k = 0; k < e->m; k++) apj_launch_step(e->st, l, nullptr, 0);
+    apj_launch_rebuild_chain(e->st, l, e->max_nbox, e->max_b);
+    APJ_CUDA(e, cudaStreamEndCapture(e->stream, &graph));
+    APJ_CUDA(e, cudaGraphInstantiate(&e->group_exec, graph, 0));
+    APJ_CUDA(e, cudaGraphDestroy(graph));
+    e->kernels_per_group = (int)dummy;
+    return APJ_OK;
+}
+
+static int launch_group(apj_engine* e) {
+    if (e->group_exec) {
+        APJ_CUDA(e, cudaGraphLaunch(e->group_exec, e->stream));
+        e->launches += e->kernels_per_group;
+    } else {
+        ApjLaunch l = launcher(e, true);
+        for (int k = 0; k < e->m; k++) apj_launch_step(e->st, l, nullptr, 0);
+        apj_launch_rebuild_chain(e->st, l, e->max_nbox, e->max_b);
+        APJ_CUDA(e, cudaGetLastError());
+    }
+    return APJ_OK;
+}
+
+static int build_group_graph(apj_engine* e);
+
+// Shared-memory tile capacity follows the decomposition: the launch configuration (and the graph)
+// is rebuilt when a rebuild produced a tile larger than the capacity (nothing was committed, the
+// system is still stale) or when the capacity is far above what the current tiles need.
+static int set_tile_cap(apj_engine* e, int cap) {
+    cap = (cap + 7) / 8 * 8;
+    if (cap > 4096) return fail(e, APJ_E_OVERFLOW, "a work block needs more than 4096 shared-memory slots (density too inhomogeneous for the tile)");
+    e->st.tile_cap = cap;
+    if (apj_configure_kernels(e->st) != 0) return fail(e, APJ_E_CUDA, "cannot reserve shared memory for the tile");
+    if (e->group_exec) { cudaGraphExecDestroy(e->group_exec); e->group_exec = nullptr; }
+    return build_group_graph(e);
+}
+// after pull_ctl: returns 1 if a tile overflow was repaired (caller must run the chain again)
+static int repair_tile_overflow(apj_engine* e, int* repaired) {
+    *repaired = 0;
+    int need = 0;
+    for (auto& c : e->hctl) if (c.overflow & 2) need = std::max(need, c.tile_max);
+    if (!need) return APJ_OK;
+    if (int rc = set_tile_cap(e, need + need / 8 + 16)) return rc;
+    for (auto& c : e->hctl) c.overflow &= ~2;
+    *repaired = 1;
+    return push_ctl(e);
+}
+static int maybe_shrink_tile_cap(apj_engine* e) {
+    if (e->cfg.tile_slots > 0) return APJ_OK;
+    int need = 0;
+    for (auto& c : e->hctl) need = std::max(need, c.tile_max);
+    const int want = need + need / 10 + 16;
+    if (need > 0 && want < e->st.tile_cap * 0.85) return set_tile_cap(e, want);
+    return APJ_OK;
+}
+
+static int check_overflow(apj_engine* e) {
+    for (size_t s = 0; s < e->hctl.size(); s++)
+        if (e->hctl[s].overflow & 1) {
+            char b[256];
+            snprintf(b, sizeof b, "Verlet list overflow in system %zu: %d neighbours within rs > max_neighbors=%d; recreate with a larger max_neighbors",
+                     s, e->hctl[s].list_max, e->st.S);
+            return fail(e, APJ_E_OVERFLOW, b);
+        }
+    return APJ_OK;
+}
+
+extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** out) {
+    if (!cfg || !L || !out) return fail(nullptr, APJ_E_INVALID, "apj_create: null argument");
+    if (cfg->n < 1 || cfg->n_systems < 1) return fail(nullptr, APJ_E_INVALID, "apj_create: n and n_systems must be >= 1");
+    if ((long long)cfg->n * cfg->n_systems > 0x7fffffffLL) return fail(nullptr, APJ_E_INVALID, "apj_create: n*n_systems exceeds 2^31-1");
+    apj_engine* e = new apj_engine;
+    e->cfg = *cfg;
+    auto bail = [&](int code) { g_create_error = e->err; apj_destroy(e); return code; };
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        e->err = "apj_create: no CUDA device (this library has no CPU fallback)";
+        return bail(APJ_E_CUDA);
+    }
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { e->err = "apj_create: cudaSetDevice failed"; return bail(APJ_E_CUDA); }
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { e->err = "apj_create: stream"; return bail(APJ_E_CUDA); }
+    cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
+
+    DevState& st = e->st;
+    st.n_sys = cfg->n_systems; st.N = (int)cfg->n; st.ntot = (long long)st.n_sys * st.N;
+    st.S = cfg->max_neighbors > 0 ? (cfg->max_neighbors + 1) / 2 * 2 : 48;
+    if (st.S > apj_max_list_capacity()) { e->err = "apj_create: max_neighbors too large (<= 96)"; return bail(APJ_E_INVALID); }
+    // lanes per particle: spread small systems over enough warps to hide latency (measured on B200)
+    st.G = cfg->lanes_per_particle;
+    if (st.G == 0) st.G = st.ntot < 150000 ? 4 : (st.ntot < 400000 ? 2 : 1);
+    if (st.G != 1 && st.G != 2 && st.G != 4 && st.G != 8) { e->err = "apj_create: lanes_per_particle must be 1, 2, 4 or 8"; return bail(APJ_E_INVALID); }
+    st.tb = st.G == 1 ? 256 : 128;
+    st.ppb = st.tb / st.G;
+    st.max_rounds = (st.S / 2 + st.G - 1) / st.G;
+    st.smem_rounds = std::min(st.max_rounds, (12 + st.G - 1) / st.G + (st.G > 2 ? 1 : 0));   // 24+ entries per particle
+    // Engine constants exactly as the reference derives them (jamming.cpp:57, :112-115, :611)
+    const double dt = cfg->dt > 0 ? cfg->dt : 0.1;
+    const double rn = cfg->rn > 0 ? cfg->rn : 2.8;
+    const double rs = (cfg->rs_factor > 0 ? cfg->rs_factor : 1.5) * rn;
+    st.dt = dt; st.rn2 = rn * rn; st.rs2 = rs * rs; st.skin = rs - rn;
+    st.seed = cfg->seed;
+    e->m = cfg->steps_per_launch > 0 ? cfg->steps_per_launch : 16;
+
+    e->hctl.assign(st.n_sys, SysCtl{});
+    long long cells = 0, cols = 0;
+    for (int s = 0; s < st.n_sys; s++) {
+        SysCtl& c = e->hctl[s];
+        c.L = L[s]; c.Lover2 = L[s] / 2.0;                  // jamming.cpp:306
+        double lp = 2 * rn;                                  // Engine::topology, jamming.cpp:361-365
+        c.b = static_cast<int>(floor(c.L / lp));
+        if (c.b < 3) { e->err = "apj_create: box too small (b = floor(L/(2 rn)) < 3 aliases neighbour cells, jamming.cpp:359)"; return bail(APJ_E_INVALID); }
+        if ((long long)c.b * c.b > 0x7ffffff0LL) { e->err = "apj_create: too many cells"; return bail(APJ_E_INVALID); }
+        c.nbox = c.b * c.b;
+        c.lp = c.L / floor(c.L / lp);
+        c.cell_base = (int)cells;
+        cells += c.nbox + 1;
+        c.col_base = (int)cols;
+        cols += c.b + 1;
+        e->max_nbox = std::max(e->max_nbox, c.nbox);
+        e->max_b = std::max(e->max_b, c.b);
+        c.stale = 0;
+    }
+    e->total_cells = cells;
+    e->total_cols = cols;
+    st.maxblk = st.N / st.ppb + e->max_b + 1;
+    {   // tile capacity: three columns x (block rows + 2 halo rows), sized from the mean cell occupancy
+        double ppc = 0;
+        for (int s = 0; s < st.n_sys; s++) ppc = std::max(ppc, (double)st.N / e->hctl[s].nbox);
+        const double mean = 3.0 * (st.ppb / ppc + 3.0) * ppc;   // three columns x (block rows + halo rows)
+        const int want = (int)(mean + 4.0 * std::sqrt(mean)) + 16;
+        st.tile_cap = cfg->tile_slots > 0 ? cfg->tile_slots : want;   // grows / shrinks with ctl.tile_max
+        st.tile_cap = std::min((st.tile_cap + 7) / 8 * 8, 4096);
+    }
+
+    int rc = APJ_OK;
+#define A(x) if (rc == APJ_OK) rc = (x)
+    A(dev_alloc(e, &st.ctl, (size_t)st.n_sys));
+    for (int h = 0; h < 2; h++) {
+        A(dev_alloc(e, &st.XY[h], (size_t)st.ntot)); A(dev_alloc(e, &st.CS[h], (size_t)st.ntot));
+        A(dev_alloc(e, &st.XR[h], (size_t)st.ntot));
+        A(dev_alloc(e, &st.RR[h], (size_t)st.ntot));  A(dev_alloc(e, &st.X0[h], (size_t)st.ntot));
+        A(dev_alloc(e, &st.XO[h], (size_t)st.ntot)); A(dev_alloc(e, &st.V[h], (size_t)st.ntot));
+        A(dev_alloc(e, &st.PHI[h], (size_t)st.ntot)); A(dev_alloc(e, &st.ID[h], (size_t)st.ntot));
+        A(dev_alloc(e, &st.BOX[h], (size_t)st.ntot));
+    }
+    A(dev_alloc(e, &st.tiles, (size_t)st.n_sys * st.maxblk));
+    A(dev_alloc(e, &st.list32, (size_t)st.n_sys * st.maxblk * st.max_rounds * st.tb));
+    A(dev_alloc(e, &st.col_blk, (size_t)cols));
+    A(dev_alloc(e, &st.cnt, (size_t)st.ntot));
+    A(dev_alloc(e, &st.boxnew, (size_t)st.ntot));
+    A(dev_alloc(e, &st.perm, (size_t)st.ntot));
+    A(dev_alloc(e, &st.cell_count, (size_t)cells));
+    A(dev_alloc(e, &st.cell_start, (size_t)cells));
+    A(dev_alloc(e, &st.cell_cursor, (size_t)cells));
+    A(dev_alloc(e, &st.partials, (size_t)st.n_sys * st.maxblk));
+    st.maxgrp = (st.maxblk + 31) / 32;
+    A(dev_alloc(e, &st.gpartials, (size_t)st.n_sys * st.maxgrp));
+    A(dev_alloc(e, &st.gticket, (size_t)st.n_sys * st.maxgrp));
+    A(dev_alloc(e, &e->d_noise, (size_t)st.ntot));
+    A(apj_obs_alloc(&e->obs, st, e->stream, e->allocs));
+#undef A
+    if (rc != APJ_OK) return bail(rc);
+    if (apj_configure_kernels(st) != 0) { e->err = "apj_create: cannot reserve shared memory for the tile (tile_slots too large?)"; return bail(APJ_E_CUDA); }
+    if (push_ctl(e) != APJ_OK) return bail(APJ_E_CUDA);
+    if (build_group_graph(e) != APJ_OK) return bail(APJ_E_CUDA);
+    *out = e;
+    return APJ_OK;
+}
+
+extern "C" int apj_destroy(apj_engine* e) {
+    if (!e) return APJ_OK;
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->group_exec) cudaGraphExecDestroy(e->group_exec);
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return APJ_OK;
+}
+
+extern "C" int apj_set_activity(apj_engine* e, const double* CFself, const double* CTnoise) {
+    if (!e) return APJ_E_INVALID;
+    if (int rc = pull_ctl(e)) return rc;
+    for (int s = 0; s < e->st.n_sys; s++) {
+        if (CFself) e->hctl[s].CFself = CFself[s];
+        if (CTnoise) e->hctl[s].CTnoise = CTnoise[s];
+    }
+    return push_ctl(e);
+}
+
+extern "C" int apj_set_ramp(apj_engine* e, int64_t tthermalize) {
+    if (!e || tthermalize < 0) return APJ_E_INVALID;
+    if (int rc = pull_ctl(e)) return rc;
+    for (auto& c : e->hctl) { c.ramp_len = tthermalize; c.ramp_t0 = c.step; }
+    return push_ctl(e);
+}
+
+extern "C" int apj_skip_self_term_once(apj_engine* e, int32_t on) {
+    if (!e) return APJ_E_INVALID;
+    if (int rc = pull_ctl(e)) return rc;
+    for (auto& c : e->hctl) c.no_self_once = on ? 1 : 0;
+    return push_ctl(e);
+}
+
+static int run_chain_now(apj_engine* e) {
+    for (int attempt = 0; attempt < 8; attempt++) {
+        apj_launch_rebuild_chain(e->st, launcher(e, true), e->max_nbox, e->max_b);
+        APJ_CUDA(e, cudaGetLastError());
+        if (int rc = pull_ctl(e)) return rc;
+        int repaired = 0;
+        if (int rc = repair_tile_overflow(e, &repaired)) return rc;
+        if (!repaired) break;
+    }
+    return check_overflow(e);
+}
+
+extern "C" int apj_upload_state(apj_engine* e, const apj_state* h) {
+    if (!e || !h) return APJ_E_INVALID;
+    if (!h->x || !h->y || !h->R) return fail(e, APJ_E_INVALID, "apj_upload_state: x, y and R are required");
+    if (!h->phi && !(h->cosp && h->sinp)) return fail(e, APJ_E_INVALID, "apj_upload_state: phi or (cosp, sinp) required");
+    DevState& st = e->st;
+    const long long n = st.ntot;
+    if (int rc = pull_ctl(e)) return rc;
+    std::vector<double2> xy(n), cs(n), rr(n), xr(n), x0(n), xo(n), v(n);
+    std::vector<double> phi(n);
+    std::vector<int> id(n), box(n);
+    for (int s = 0; s < st.n_sys; s++) {
+        SysCtl& c = e->hctl[s];
+        double cx = 0.0, cy = 0.0;
+        for (int i = 0; i < st.N; i++) {
+            const long long g = (long long)s * st.N + i;
+            xy[g] = make_double2(h->x[g], h->y[g]);
+            phi[g] = h->phi ? h->phi[g] : std::atan2(h->sinp[g], h->cosp[g]);
+            cs[g].x = h->cosp ? h->cosp[g] : std::cos(h->phi[g]);   // jamming.cpp:332-333
+            cs[g].y = h->sinp ? h->sinp[g] : std::sin(h->phi[g]);
+            xr[g] = h->x_real ? make_double2(h->x_real[g], h->y_real[g]) : make_double2(h->x[g], h->y[g]);
+            x0[g] = h->x0 ? make_double2(h->x0[g], h->y0[g]) : xr[g];
+            xo[g] = h->x_old ? make_double2(h->x_old[g], h->y_old[g]) : make_double2(h->x[g], h->y[g]);
+            v[g] = h->vx ? make_double2(h->vx[g], h->vy[g]) : make_double2(0.0, 0.0);
+            rr[g] = make_double2(h->R[g], 1.0 / h->R[g]);            // Cell::R, Cell::Rinv (jamming.cpp:297-298)
+            id[g] = i;
+            int bx = h->box ? h->box[g] : -1;
+            if (bx >= 0 && bx < c.nbox) { const int qx = bx % c.b, qy = bx / c.b; bx = qy + qx * c.b; } else bx = -1;
+            box[g] = bx;
+            if (!(h->R[g] > 0.0)) return fail(e, APJ_E_INVALID, "apj_upload_state: radii must be positive");
+        }
+        for (int i = 0; i < st.N; i++) cx += xr[(long long)s * st.N + i].x;   // calculate_COM order (:761-774)
+        for (int i = 0; i < st.N; i++) cy += xr[(long long)s * st.N + i].y;
+        c.COM[0] = cx / st.N; c.COM[1] = cy / st.N;
+        c.COM_old[0] = c.COM0[0] = c.COM[0]; c.COM_old[1] = c.COM0[1] = c.COM[1];
+        c.cur = 0; c.gen = 0; c.stale = 1; c.save_old = 0; c.ticket = 0; c.overflow = 0; c.list_max = 0;
+        c.target = c.step;
+    }
+    cudaStream_t q = e->stream;
+    APJ_CUDA(e, cudaMemcpyAsync(st.XY[0], xy.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.CS[0], cs.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.XR[0], xr.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.X0[0], x0.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.XO[0], xo.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.V[0], v.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.RR[0], rr.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.PHI[0], phi.data(), n * sizeof(double), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.ID[0], id.data(), n * sizeof(int), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.BOX[0], box.data(), n * sizeof(int), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemsetAsync(st.cell_count, 0, sizeof(int) * e->total_cells, q));
+    if (int rc = push_ctl(e)) return rc;
+    e->have_state = true;
+    return run_chain_now(e);   // assignCellsToGrid + buildVerletLists (start() :184-185)
+}
+
+extern "C" int apj_download_state(apj_engine* e, apj_state* h) {
+    if (!e || !h) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_download_state: no state uploaded");
+    DevState& st = e->st;
+    const long long n = st.ntot;
+    if (int rc = pull_ctl(e)) return rc;
+    // all systems share parity only if they committed the same number of steps; handle per system
+    std::vector<double2> xy(n), cs(n), rr(n), xr(n), x0(n), xo(n), v(n);
+    std::vector<double> phi(n);
+    std::vector<int> id(n), box(n);
+    cudaStream_t q = e->stream;
+    for (int s = 0; s < st.n_sys; s++) {
+        const SysCtl& c = e->hctl[s];
+        const long long o = (long long)s * st.N;
+        const size_t N = st.N;
+        APJ_CUDA(e, cudaMemcpyAsync(xy.data() + o, st.XY[c.cur] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
+        APJ_CUDA(e, cudaMemcpyAsync(cs.data() + o, st.CS[c.cur] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
+        APJ_CUDA(e, cudaMemcpyAsync(xr.data() + o, st.XR[c.cur] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
+        APJ_CUDA(e, cudaMemcpyAsync(x0.data() + o, st.X0[c.gen] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
+        APJ_CUDA(e, cudaMemcpyAsync(xo.data() + o, st.XO[c.gen] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
+        APJ_CUDA(e, cudaMemcpyAsync(v.data() + o, st.V[c.gen] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
+        APJ_CUDA(e, cudaMemcpyAsync(rr.data() + o, st.RR[c.gen] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
+        APJ_CUDA(e, cudaMemcpyAsync(phi.data() + o, st.PHI[c.gen] + o, N * sizeof(double), cudaMemcpyDeviceToHost, q));
+        APJ_CUDA(e, cudaMemcpyAsync(id.data() + o, st.ID[c.gen] + o, N * sizeof(int), cudaMemcpyDeviceToHost, q));
+        APJ_CUDA(e, cudaMemcpyAsync(box.data() + o, st.BOX[c.gen] + o, N * sizeof(int), cudaMemcpyDeviceToHost, q));
+    }
+    APJ_CUDA(e, cudaStreamSynchronize(q));
+    for (int s = 0; s < st.n_sys; s++) {
+        const SysCtl& c = e->hctl[s];
+        for (int k = 0; k < st.N; k++) {
+            const long long g = (long long)s * st.N + k;
+            const long long d = (long long)s * st.N + id[g];
+            if (h->x) h->x[d] = xy[g].x;           if (h->y) h->y[d] = xy[g].y;
+            if (h->cosp) h->cosp[d] = cs[g].x;     if (h->sinp) h->sinp[d] = cs[g].y;
+            if (h->x_real) h->x_real[d] = xr[g].x; if (h->y_real) h->y_real[d] = xr[g].y;
+            if (h->x0) h->x0[d] = x0[g].x;         if (h->y0) h->y0[d] = x0[g].y;
+            if (h->x_old) h->x_old[d] = xo[g].x;   if (h->y_old) h->y_old[d] = xo[g].y;
+            if (h->vx) h->vx[d] = v[g].x;          if (h->vy) h->vy[d] = v[g].y;
+            if (h->R) h->R[d] = rr[g].x;              if (h->phi) h->phi[d] = phi[g];
+            if (h->box) { const int bi = box[g]; h->box[d] = bi < 0 ? -1 : (bi / c.b) + (bi % c.b) * c.b; }
+        }
+    }
+    return APJ_OK;
+}
+
+extern "C" int apj_set_com(apj_engine* e, int32_t s, const double* com, const double* com0, const double* com_old) {
+    if (!e || s < 0 || s >= e->st.n_sys) return APJ_E_INVALID;
+    if (int rc = pull_ctl(e)) return rc;
+    SysCtl& c = e->hctl[s];
+    if (com) { c.COM[0] = com[0]; c.COM[1] = com[1]; }
+    if (com0) { c.COM0[0] = com0[0]; c.COM0[1] = com0[1]; }
+    if (com_old) { c.COM_old[0] = com_old[0]; c.COM_old[1] = com_old[1]; }
+    return push_ctl(e);
+}
+extern "C" int apj_get_com(apj_engine* e, int32_t s, double* com, double* com0, double* com_old) {
+    if (!e || s < 0 || s >= e->st.n_sys) return APJ_E_INVALID;
+    if (int rc = pull_ctl(e)) return rc;
+    const SysCtl& c = e->hctl[s];
+    if (com) { com[0] = c.COM[0]; com[1] = c.COM[1]; }
+    if (com0) { com0[0] = c.COM0[0]; com0[1] = c.COM0[1]; }
+    if (com_old) { com_old[0] = c.COM_old[0]; com_old[1] = c.COM_old[1]; }
+    return APJ_OK;
+}
+
+__global__ void apj_mark_origin_kernel(const DevState st) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= st.ntot) return;
+    const SysCtl* ctl = st.ctl + (int)(g / st.N);
+    const double2 x = st.XY[ctl->cur][g];
+    st.XR[ctl->cur][g] = x;     // x_real = x   (jamming.cpp:193-196)
+    st.X0[ctl->gen][g] = x;     // x0 = x
+    st.XO[ctl->gen][g] = x;     // saveOldPositions (:203)
+}
+
+extern "C" int apj_mark_origin(apj_engine* e) {
+    if (!e) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_mark_origin: no state uploaded");
+    DevState& st = e->st;
+    apj_mark_origin_kernel<<<(unsigned)((st.ntot + 255) / 256), 256, 0, e->stream>>>(st);
+    e->launches++;
+    // COM = mean(x_real) in the deterministic two-level order of the step kernel
+    std::vector<double> com(2 * st.n_sys);
+    if (int rc = apj_obs_com(&e->obs, st, e->stream, &e->launches, com.data())) return fail(e, rc, "apj_mark_origin: COM reduction failed");
+    if (int rc = pull_ctl(e)) return rc;
+    for (int s = 0; s < st.n_sys; s++) {
+        SysCtl& c = e->hctl[s];
+        c.COM[0] = com[2 * s]; c.COM[1] = com[2 * s + 1];
+        c.COM0[0] = c.COM_old[0] = c.COM[0]; c.COM0[1] = c.COM_old[1] = c.COM[1];
+    }
+    return push_ctl(e);
+}
+
+extern "C" int apj_sync(apj_engine* e) {
+    if (!e) return APJ_E_INVALID;
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    return APJ_OK;
+}
+
+static bool all_done(const apj_engine* e, long long* remaining) {
+    long long r = 0;
+    for (const auto& c : e->hctl) r = std::max(r, c.target - c.step);
+    *remaining = r;
+    return r == 0;
+}
+
+extern "C" int apj_step(apj_engine* e, int64_t n_steps) {
+    if (!e || n_steps < 0) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_step: no state uploaded");
+    if (n_steps == 0) return APJ_OK;
+    if (int rc = maybe_shrink_tile_cap(e)) return rc;
+    DevState& st = e->st;
+    apj_add_target_kernel<<<(st.n_sys + 63) / 64, 64, 0, e->stream>>>(st.ctl, st.n_sys, n_steps);
+    e->launches++;
+    long long remaining = n_steps;
+    for (int guard = 0; guard < 1 << 20; guard++) {
+        const long long groups = (remaining + e->m - 1) / e->m + (guard ? 0 : 1);
+        for (long long k = 0; k < groups; k++)
+            if (int rc = launch_group(e)) return rc;
+        if (int rc = pull_ctl(e)) return rc;
+        int repaired = 0;
+        if (int rc = repair_tile_overflow(e, &repaired)) return rc;
+        if (int rc = check_overflow(e)) return rc;
+        if (all_done(e, &remaining)) return APJ_OK;
+    }
+    return fail(e, APJ_E_STATE, "apj_step: no progress");
+}
+
+extern "C" int apj_step_injected(apj_engine* e, const double* noise) {
+    if (!e || !noise) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_step_injected: no state uploaded");
+    DevState& st = e->st;
+    APJ_CUDA(e, cudaMemcpyAsync(e->d_noise, noise, sizeof(double) * st.ntot, cudaMemcpyHostToDevice, e->stream));
+    apj_add_target_kernel<<<(st.n_sys + 63) / 64, 64, 0, e->stream>>>(st.ctl, st.n_sys, 1);
+    e->launches++;
+    ApjLaunch l = launcher(e, true);
+    for (int attempt = 0; attempt < 12; attempt++) {
+        apj_launch_step(st, l, e->d_noise, 1);
+        apj_launch_rebuild_chain(st, l, e->max_nbox, e->max_b);
+        APJ_CUDA(e, cudaGetLastError());
+        if (int rc = pull_ctl(e)) return rc;
+        int repaired = 0;
+        if (int rc = repair_tile_overflow(e, &repaired)) return rc;
+        if (int rc = check_overflow(e)) return rc;
+        long long remaining;
+        if (all_done(e, &remaining)) return APJ_OK;
+    }
+    return fail(e, APJ_E_STATE, "apj_step_injected: step did not commit");
+}
+
+extern "C" int apj_force_rebuild(apj_engine* e) {
+    if (!e) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_force_rebuild: no state uploaded");
+    if (int rc = pull_ctl(e)) return rc;
+    for (auto& c : e->hctl) { c.stale = 1; c.save_old = 0; }
+    if (int rc = push_ctl(e)) return rc;
+    return run_chain_now(e);
+}
+
+extern "C" int apj_get_counters(apj_engine* e, int32_t s, int64_t* o) {
+    if (!e || !o || s < 0 || s >= e->st.n_sys) return APJ_E_INVALID;
+    if (int rc = pull_ctl(e)) return rc;
+    const SysCtl& c = e->hctl[s];
+    o[0] = c.step; o[1] = c.reset_counter; o[2] = c.n_rebuilds; o[3] = c.list_max; o[4] = c.overflow;
+    o[5] = e->launches; o[6] = c.n_discarded; o[7] = c.nbox;
+    return APJ_OK;
+}
+extern "C" int apj_get_tuning(apj_engine* e, int32_t* o) {
+    if (!e || !o) return APJ_E_INVALID;
+    if (int rc = pull_ctl(e)) return rc;
+    int tm = 0, nb = 0;
+    for (auto& c : e->hctl) { tm = std::max(tm, c.tile_max); nb += c.nblk; }
+    o[0] = e->st.G; o[1] = e->st.tb; o[2] = e->st.ppb; o[3] = e->st.tile_cap; o[4] = tm;
+    o[5] = (int)(e->st.tile_cap * 48 + (size_t)e->st.smem_rounds * e->st.tb * 4 + (size_t)e->st.ppb * 32); o[6] = nb; o[7] = e->m;
+    return APJ_OK;
+}
+extern "C" int apj_set_reset_counter(apj_engine* e, int32_t s, int64_t v) {
+    if (!e || s < 0 || s >= e->st.n_sys) return APJ_E_INVALID;
+    if (int rc = pull_ctl(e)) return rc;
+    e->hctl[s].reset_counter = v;
+    return push_ctl(e);
+}
+extern "C" int apj_get_geometry(apj_engine* e, int32_t s, double* o) {
+    if (!e || !o || s < 0 || s >= e->st.n_sys) return APJ_E_INVALID;
+    const SysCtl& c = e->hctl[s];
+    o[0] = c.L; o[1] = c.Lover2; o[2] = c.lp; o[3] = c.b; o[4] = c.nbox;
+    return APJ_OK;
+}
+
+extern "C" int apj_get_pair_list(apj_engine* e, int32_t s, int64_t* offsets, int32_t* idx, int64_t cap, int64_t* total) {
+    if (!e || s < 0 || s >= e->st.n_sys || !total) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_get_pair_list: no state uploaded");
+    DevState& st = e->st;
+    if (int rc = pull_ctl(e)) return rc;
+    const SysCtl& c = e->hctl[s];
+    const long long o = (long long)s * st.N;
+    const size_t N = st.N;
+    const size_t words_per_blk = (size_t)st.max_rounds * st.tb;
+    std::vector<int> id(N), cnt(N);
+    std::vector<TileDesc> tiles(c.nblk);
+    std::vector<unsigned> lst(words_per_blk * c.nblk);
+    APJ_CUDA(e, cudaMemcpyAsync(id.data(), st.ID[c.gen] + o, N * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaMemcpyAsync(cnt.data(), st.cnt + o, N * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaMemcpyAsync(tiles.data(), st.tiles + (size_t)s * st.maxblk, c.nblk * sizeof(TileDesc), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaMemcpyAsync(lst.data(), st.list32 + (size_t)s * st.maxblk * words_per_blk, lst.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    // decode tile slots -> particle index -> id; keep partners with larger id, ascending
+    std::vector<std::vector<int>> half(N);
+    size_t covered = 0;
+    for (int blk = 0; blk < c.nblk; blk++) {
+        const TileDesc& d = tiles[blk];
+        for (int t = 0; t < d.n; t++, covered++) {
+            const long long g = d.g0 + t - o;
+            if (g < 0 || g >= (long long)N) return fail(e, APJ_E_STATE, "apj_get_pair_list: tile outside its system");
+            for (int k = 0; k < cnt[g]; k++) {
+                const int wi = k >> 1;
+                const unsigned w = lst[blk * words_per_blk + (size_t)(wi / st.G) * st.tb + (size_t)t * st.G + (wi % st.G)];
+                int slot = (k & 1) ? (int)(w >> 16) : (int)(w & 0xffffu);
+                long long j = -1;
+                for (int p = 0; p < (d.info & 0xff); p++) {
+                    if (slot < d.plen[p]) { j = (long long)d.pstart[p] + slot - o; break; }
+                    slot -= d.plen[p];
+                }
+                if (j < 0 || j >= (long long)N) return fail(e, APJ_E_STATE, "apj_get_pair_list: list entry outside its tile");
+                if (id[j] > id[g]) half[id[g]].push_back(id[j]);
+            }
+        }
+    }
+    if (covered != N) return fail(e, APJ_E_STATE, "apj_get_pair_list: work blocks do not cover the system");
+    int64_t tot = 0;
+    for (size_t i = 0; i < N; i++) {
+        std::sort(half[i].begin(), half[i].end());
+        if (offsets) offsets[i] = tot;
+        for (int j : half[i]) { if (idx && tot < cap) idx[tot] = j; tot++; }
+    }
+    if (offsets) offsets[N] = tot;
+    *total = tot;
+    return APJ_OK;
+}
+
+extern "C" int apj_get_cell_lists(apj_engine* e, int32_t s, int64_t* offsets, int32_t* idx) {
+    if (!e || s < 0 || s >= e->st.n_sys || !offsets || !idx) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_get_cell_lists: no state uploaded");
+    DevState& st = e->st;
+    if (int rc = pull_ctl(e)) return rc;
+    const SysCtl& c = e->hctl[s];
+    const long long o = (long long)s * st.N;
+    const size_t N = st.N;
+    std::vector<int> id(N), box(N);
+    APJ_CUDA(e, cudaMemcpyAsync(id.data(), st.ID[c.gen] + o, N * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaMemcpyAsync(box.data(), st.BOX[c.gen] + o, N * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    std::vector<int> ref_box(N);
+    for (size_t g = 0; g < N; g++) ref_box[id[g]] = (box[g] / c.b) + (box[g] % c.b) * c.b;   // -> i + j*b
+    std::vector<int64_t> count(c.nbox + 1, 0);
+    for (size_t i = 0; i < N; i++) count[ref_box[i] + 1]++;
+    for (int p = 0; p < c.nbox; p++) count[p + 1] += count[p];
+    for (int p = 0; p <= c.nbox; p++) offsets[p] = count[p];
+    std::vector<int64_t> fill(count.begin(), count.end() - 1);
+    for (size_t i = 0; i < N; i++) idx[fill[ref_box[i]]++] = (int)i;
+    return APJ_OK;
+}
+
+// ---- observables: thin wrappers over apj_observe.cu ---------------------------------------
+#define APJ_NEED_STATE(name) \
+    if (!e) return APJ_E_INVALID; \
+    if (!e->have_state) return fail(e, APJ_E_STATE, name ": no state uploaded")
+#define APJ_OBS(call) do { int _rc = (call); if (_rc) return fail(e, _rc, cudaGetErrorString(cudaGetLastError())); return APJ_OK; } while (0)
+
+extern "C" int apj_order_orientation(apj_engine* e, double* order, double* orient) {
+    APJ_NEED_STATE("apj_order_orientation");
+    APJ_OBS(apj_obs_order(&e->obs, e->st, e->stream, &e->launches, order, orient));
+}
+extern "C" int apj_msd(apj_engine* e, double* msd) {
+    APJ_NEED_STATE("apj_msd");
+    APJ_OBS(apj_obs_msd(&e->obs, e->st, e->stream, &e->launches, msd));
+}
+extern "C" int apj_fluct_area(apj_engine* e, const double* radius, double* area) {
+    APJ_NEED_STATE("apj_fluct_area");
+    if (!radius || !area) return APJ_E_INVALID;
+    APJ_OBS(apj_obs_fluct(&e->obs, e->st, e->stream, &e->launches, radius, area));
+}
+extern "C" int apj_spatial_correlations(apj_engine* e, double cutoff, double* counts, double* ori, double* vel, double* pair) {
+    APJ_NEED_STATE("apj_spatial_correlations");
+    if (!(cutoff > 0) || !counts || !ori || !vel || !pair) return APJ_E_INVALID;
+    // nc*dr_c must not exceed the cutoff, or the reference's boxPairs filter (jamming.cpp:460-479)
+    // would decide membership of the last bin; its own settings (20, 140) are multiples of 2.
+    if (std::fmod(cutoff, 2.0) != 0.0) return fail(e, APJ_E_INVALID, "apj_spatial_correlations: cutoff must be a multiple of dr_c = 2");
+    APJ_OBS(apj_obs_spatial(&e->obs, e->st, e->stream, &e->launches, e->hctl.data(), cutoff, counts, ori, vel, pair, e->allocs));
+}
+extern "C" int apj_vel_hist(apj_engine* e, const double* dv, int64_t* hist100) {
+    APJ_NEED_STATE("apj_vel_hist");
+    if (!dv || !hist100) return APJ_E_INVALID;
+    APJ_OBS(apj_obs_velhist(&e->obs, e->st, e->stream, &e->launches, dv, hist100));
+}
+extern "C" int apj_occupancy_hist(apj_engine* e, int64_t* hist50) {
+    APJ_NEED_STATE("apj_occupancy_hist");
+    if (!hist50) return APJ_E_INVALID;
+    APJ_OBS(apj_obs_occupancy(&e->obs, e->st, e->stream, &e->launches, hist50));
+}
+
+extern "C" int apj_timer_begin(apj_engine* e) {
+    if (!e) return APJ_E_INVALID;
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    APJ_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    return APJ_OK;
+}
+extern "C" int apj_timer_end(apj_engine* e, float* ms) {
+    if (!e || !ms) return APJ_E_INVALID;
+    APJ_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    APJ_CUDA(e, cudaEventSynchronize(e->ev1));
+    APJ_CUDA(e, cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return APJ_OK;
+}
+
+extern "C" int apj_time_step_kernel(apj_engine* e, int64_t n, float* mean_ms, int64_t* committed) {
+    if (!e || n < 1 || n > 4096 || !mean_ms) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_time_step_kernel: no state uploaded");
+    DevState& st = e->st;
+    if (int rc = pull_ctl(e)) return rc;
+    const long long step0 = e->hctl[0].step;
+    std::vector<cudaEvent_t> ev(2 * n);
+    for (auto& x : ev) APJ_CUDA(e, cudaEventCreate(&x));
+    ApjLaunch l = launcher(e, true);
+    for (int64_t k = 0; k < n; k++) {
+        apj_add_target_kernel<<<(st.n_sys + 63) / 64, 64, 0, e->stream>>>(st.ctl, st.n_sys, 1);
+        e->launches++;
+        APJ_CUDA(e, cudaEventRecord(ev[2 * k], e->stream));
+        apj_launch_step(st, l, nullptr, 0);
+        APJ_CUDA(e, cudaEventRecord(ev[2 * k + 1], e->stream));
+        apj_launch_rebuild_chain(st, l, e->max_nbox, e->max_b);
+    }
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    double tot = 0;
+    for (int64_t k = 0; k < n; k++) { float ms = 0; APJ_CUDA(e, cudaEventElapsedTime(&ms, ev[2 * k], ev[2 * k + 1])); tot += ms; }
+    for (auto& x : ev) cudaEventDestroy(x);
+    *mean_ms = (float)(tot / n);
+    if (int rc = pull_ctl(e)) return rc;
+    if (committed) *committed = e->hctl[0].step - step0;
+    // finish any step that was rolled back on the last launch
+    long long remaining;
+    if (!all_done(e, &remaining)) {
+        for (int a = 0; a < 4 && !all_done(e, &remaining); a++) {
+            apj_launch_step(st, l, nullptr, 0);
+            apj_launch_rebuild_chain(st, l, e->max_nbox, e->max_b);
+            if (int rc = pull_ctl(e)) return rc;
+        }
+    }
+    return check_overflow(e);
+}

@@ -1,0 +1,417 @@
+// Rebuild chain: assignCellsToGrid + buildVerletLists (+ saveOldPositions when the skin test
+// fired) of the reference (code/jam/jamming.cpp:527-548, :550-585, :825-835), re-designed as a
+// counting sort that physically re-orders every particle array into cell order:
+//
+//   bin_count    exact nearest-box-centre binning + atomic histogram of cells
+//   cell_scan    exclusive prefix scan of the histogram -> cell_start / cell_cursor
+//   scatter      slot = atomicAdd(cursor[cell]) -> perm
+//   cell_sort    sort each cell's slots by particle id (== Box::CellList ascending order;
+//                makes the layout, and with it every reduction order, deterministic)
+//   reorder      gather all SoA arrays through perm into the other ping-pong half
+//   make_tiles   cut every cell column into work blocks of <= ppb particles and record, per
+//                block, the contiguous particle runs that cover all adjacent cells (TileDesc)
+//   verlet_build 3x3 cell sweep, d2 < rs2, full list sorted by distance, stored as tile slots
+//   finish       flip parities, COM_old = COM, resetCounter++, clear `stale`
+//
+// Every kernel exits at once for systems whose ctl.stale is 0, so the chain can sit in the
+// step graph unconditionally and costs a few empty launches when no rebuild is pending.
+#include "apj_device.cuh"
+
+namespace {
+
+constexpr int RB_BLOCK = 128;
+constexpr int SCAN_BLOCK = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int MAX_S = 96;  // compile-time bound of DevState::S
+
+// ---- assignCellsToGrid (jamming.cpp:527-548) ---------------------------------------------
+// The reference scans ALL boxes for the nearest centre with strict '<' starting from
+// r2 = lp*lp*0.25*NDIM; only the 3x3 boxes around the floor-binned one can win, and they are
+// visited here in the same ascending box order (i + j*b), so ties resolve identically. If no
+// box wins (particle exactly on a 4-corner) the particle keeps its previous box, as there.
+__device__ __forceinline__ double box_centre(int i, double L, double Lh, int b) {
+    const double mn = -Lh + i * L / b;         // grid[p].min (jamming.cpp:379-380)
+    const double mx = -Lh + (i + 1) * L / b;   // grid[p].max (:381-382)
+    return (mn + mx) / 2.;                     // :385
+}
+
+__global__ void __launch_bounds__(RB_BLOCK) apj_bin_count_kernel(const DevState st, const int bps) {
+    const int sys = blockIdx.x / bps;
+    const SysCtl* __restrict__ ctl = st.ctl + sys;
+    if (!ctl->stale) return;
+    const int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x;
+    if (i >= st.N) return;
+    const long long g = (long long)sys * st.N + i;
+    const int b = ctl->b;
+    const double L = ctl->L, Lh = ctl->Lover2, lp = ctl->lp;
+    const double2 me = st.XY[ctl->cur][g];
+    const int gx = (int)floor((me.x + Lh) / lp), gy = (int)floor((me.y + Lh) / lp);
+    double r2 = lp * lp * 0.25 * 2;
+    int best = st.BOX[ctl->gen][g];
+    for (int qy = gy - 1; qy <= gy + 1; qy++) {
+        if (qy < 0 || qy >= b) continue;
+        const double dry = me.y - box_centre(qy, L, Lh, b);
+        for (int qx = gx - 1; qx <= gx + 1; qx++) {
+            if (qx < 0 || qx >= b) continue;
+            const double drx = me.x - box_centre(qx, L, Lh, b);
+            double d2 = 0.0;
+            d2 += drx * drx;
+            d2 += dry * dry;
+            if (d2 < r2) { r2 = d2; best = qy + qx * b; }  // internal numbering: columns contiguous
+        }
+    }
+    if (best < 0) {  // reference would index grid[-1]; clamp to the floor bin instead
+        const int cx = min(max(gx, 0), b - 1), cy = min(max(gy, 0), b - 1);
+        best = cy + cx * b;
+    }
+    st.boxnew[g] = best;
+    atomicAdd(st.cell_count + ctl->cell_base + best, 1);
+}
+
+// ---- exclusive scan of one system's cell histogram (one block per system) -------------------
+__global__ void __launch_bounds__(SCAN_BLOCK) apj_cell_scan_kernel(const DevState st) {
+    const int sys = blockIdx.x;
+    const SysCtl* __restrict__ ctl = st.ctl + sys;
+    if (!ctl->stale) return;
+    const int nbox = ctl->nbox;
+    int* __restrict__ count = st.cell_count + ctl->cell_base;
+    int* __restrict__ start = st.cell_start + ctl->cell_base;
+    int* __restrict__ cursor = st.cell_cursor + ctl->cell_base;
+    __shared__ int s_warp[SCAN_BLOCK / 32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = sys * st.N;  // absolute particle index of the system's first slot
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < nbox; base += SCAN_BLOCK * SCAN_ITEMS) {
+        int v[SCAN_ITEMS];
+        int tsum = 0;
+        const int first = base + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            v[k] = (first + k < nbox) ? count[first + k] : 0;
+            tsum += v[k];
+        }
+        int inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            s_warp[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        int run = carry + (wid ? s_warp[wid - 1] : 0) + inc - tsum;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (first + k < nbox) {
+                start[first + k] = run;
+                cursor[first + k] = run;
+                count[first + k] = 0;  // leave the histogram clean for the next rebuild
+            }
+            run += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) s_carry = carry + s_warp[SCAN_BLOCK / 32 - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) start[nbox] = s_carry;
+}
+
+__global__ void __launch_bounds__(RB_BLOCK) apj_scatter_kernel(const DevState st, const int bps) {
+    const int sys = blockIdx.x / bps;
+    const SysCtl* __restrict__ ctl = st.ctl + sys;
+    if (!ctl->stale) return;
+    const int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x;
+    if (i >= st.N) return;
+    const long long g = (long long)sys * st.N + i;
+    const int slot = atomicAdd(st.cell_cursor + ctl->cell_base + st.boxnew[g], 1);
+    st.perm[slot] = (int)g;
+}
+
+// ---- per-cell sort of the slots by original particle id (CellList order, jamming.cpp:546) ----
+__global__ void __launch_bounds__(RB_BLOCK) apj_cell_sort_kernel(const DevState st) {
+    const int sys = blockIdx.y;
+    const SysCtl* __restrict__ ctl = st.ctl + sys;
+    if (!ctl->stale) return;
+    const int c = blockIdx.x * RB_BLOCK + threadIdx.x;
+    if (c >= ctl->nbox) return;
+    const int* __restrict__ idv = st.ID[ctl->gen];
+    const int* __restrict__ start = st.cell_start + ctl->cell_base;
+    const int s0 = start[c], n = start[c + 1] - s0;
+    int* __restrict__ p = st.perm + s0;
+    for (int a = 1; a < n; a++) {   // insertion sort; n is ~9 (max ~14 at phi <= 1)
+        const int pa = p[a];
+        const int ka = idv[pa];
+        int q = a - 1;
+        while (q >= 0 && idv[p[q]] > ka) { p[q + 1] = p[q]; q--; }
+        p[q + 1] = pa;
+    }
+}
+
+__global__ void __launch_bounds__(RB_BLOCK) apj_reorder_kernel(const DevState st, const int bps) {
+    const int sys = blockIdx.x / bps;
+    const SysCtl* __restrict__ ctl = st.ctl + sys;
+    if (!ctl->stale) return;
+    const int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x;
+    if (i >= st.N) return;
+    const long long k = (long long)sys * st.N + i;
+    const int cur = ctl->cur, gen = ctl->gen;
+    const int src = st.perm[k];
+    const double2 p = st.XY[cur][src];
+    st.XY[cur ^ 1][k] = p;
+    st.CS[cur ^ 1][k] = st.CS[cur][src];
+    st.XR[cur ^ 1][k] = st.XR[cur][src];
+    st.RR[gen ^ 1][k] = st.RR[gen][src];
+    st.X0[gen ^ 1][k] = st.X0[gen][src];
+    st.XO[gen ^ 1][k] = ctl->save_old ? p : st.XO[gen][src];  // saveOldPositions (jamming.cpp:825-835)
+    st.V[gen ^ 1][k] = st.V[gen][src];
+    st.PHI[gen ^ 1][k] = st.PHI[gen][src];
+    st.ID[gen ^ 1][k] = st.ID[gen][src];
+    st.BOX[gen ^ 1][k] = st.boxnew[src];
+}
+
+// ---- work decomposition: blocks of <= ppb particles inside one cell column ---------------
+__device__ __forceinline__ void add_piece(TileDesc& d, int& npieces, int& slots, int p0, int p1) {
+    if (p1 <= p0) return;
+    d.pstart[npieces] = p0;
+    d.plen[npieces] = p1 - p0;
+    npieces++;
+    slots += p1 - p0;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevState st) {
+    const int sys = blockIdx.x;
+    SysCtl* __restrict__ ctl = st.ctl + sys;
+    if (!ctl->stale) return;
+    const int b = ctl->b;
+    const int* __restrict__ start = st.cell_start + ctl->cell_base;
+    int* __restrict__ col_blk = st.col_blk + ctl->col_base;
+    const int* __restrict__ box = st.BOX[ctl->gen ^ 1];   // the half reorder just wrote
+    __shared__ int s_warp[SCAN_BLOCK / 32];
+    __shared__ int s_carry, s_tile_max, s_over;
+    if (threadIdx.x == 0) { s_carry = 0; s_tile_max = 0; s_over = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ppb = st.ppb;
+    // exclusive scan over columns of ceil(n_X / ppb)
+    for (int base = 0; base < b; base += SCAN_BLOCK) {
+        const int X = base + threadIdx.x;
+        const int nb = (X < b) ? (start[(X + 1) * b] - start[X * b] + ppb - 1) / ppb : 0;
+        int inc = nb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (X < b) col_blk[X] = carry + (wid ? s_warp[wid - 1] : 0) + inc - nb;
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) s_carry = carry + s_warp[SCAN_BLOCK / 32 - 1];
+        __syncthreads();
+    }
+    const int nblk = s_carry;
+    if (threadIdx.x == 0) col_blk[b] = nblk;
+    // descriptors: one thread per column walks that column's blocks
+    int tile_max = 0, over = 0;
+    for (int X = threadIdx.x; X < b; X += SCAN_BLOCK) {
+        const int c0 = start[X * b], c1 = start[(X + 1) * b];
+        int blk = col_blk[X];
+        for (int g0 = c0; g0 < c1; g0 += ppb, blk++) {
+            TileDesc d;
+            d.g0 = g0; d.n = min(ppb, c1 - g0); d.own_slot = 0;
+            for (int p = 0; p < APJ_MAX_PIECES; p++) { d.pstart[p] = 0; d.plen[p] = 0; }
+            const int cy0 = box[g0] - X * b, cy1 = box[g0 + d.n - 1] - X * b;
+            int slots = 0, npieces = 0;
+            // minimum-image wraps can only fire in blocks that touch the periodic seam
+            int wraps = (b < 7 || X == 0 || X == b - 1 || cy0 == 0 || cy1 == b - 1) ? 1 : 0;
+            for (int dx = -1; dx <= 1; dx++) {
+                int Xd = X + dx;
+                if (Xd < 0) Xd += b; else if (Xd >= b) Xd -= b;
+                const int* __restrict__ cs = start + Xd * b;
+                const int lo = cy0 - 1, hi = cy1 + 1;
+                const int before = slots;
+                int piece_of_own = -1;
+                if (hi - lo + 1 >= b) {                    // rows cover the whole column
+                    piece_of_own = npieces; add_piece(d, npieces, slots, cs[0], cs[b]);
+                } else if (lo < 0) {                       // wraps below: rows [0..hi] then [b-1]
+                    piece_of_own = npieces; add_piece(d, npieces, slots, cs[0], cs[hi + 1]);
+                    add_piece(d, npieces, slots, cs[lo + b], cs[b]);
+                } else if (hi > b - 1) {                   // wraps above: rows [lo..b-1] then [0]
+                    piece_of_own = npieces; add_piece(d, npieces, slots, cs[lo], cs[b]);
+                    add_piece(d, npieces, slots, cs[0], cs[hi - b + 1]);
+                } else {
+                    piece_of_own = npieces; add_piece(d, npieces, slots, cs[lo], cs[hi + 1]);
+                }
+                if (dx == 0) {   // the block's own particles sit in the first piece of the middle column
+                    int off = before;
+                    (void)piece_of_own;
+                    d.own_slot = off + (g0 - d.pstart[piece_of_own]);
+                }
+            }
+            d.info = npieces | (wraps << 8);           // list words are filled in by verlet_build
+            tile_max = max(tile_max, slots);
+            if (slots > st.tile_cap || slots > 65535) over = 1;
+            st.tiles[(long long)sys * st.maxblk + blk] = d;
+        }
+    }
+    if (tile_max) atomicMax(&s_tile_max, tile_max);
+    if (over) atomicOr(&s_over, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ctl->nblk = nblk;
+        ctl->tile_max = s_tile_max;
+        if (s_over) ctl->overflow |= 2;
+    }
+}
+
+// ---- buildVerletLists (jamming.cpp:550-585) as a full, distance-sorted list -------------------
+// Candidates are the 3x3 cells around the particle's cell; in the internal numbering
+// (cy + cx*b) each of the three columns is one contiguous run of particles unless it wraps in y.
+// Entries are stored as 16-bit slots of the block's tile (TileDesc), two per 32-bit word.
+__global__ void __launch_bounds__(APJ_TB_MAX) apj_verlet_build_kernel(const DevState st) {
+    const int sys = blockIdx.x / st.maxblk;
+    const int blk = blockIdx.x - sys * st.maxblk;
+    SysCtl* __restrict__ ctl = st.ctl + sys;
+    if (!ctl->stale || blk >= ctl->nblk || (ctl->overflow & 2)) return;
+    __shared__ TileDesc sd;
+    __shared__ int s_lwords;
+    const long long bg = (long long)sys * st.maxblk + blk;
+    if (threadIdx.x < 16) reinterpret_cast<int*>(&sd)[threadIdx.x] = reinterpret_cast<const int*>(st.tiles + bg)[threadIdx.x];
+    if (threadIdx.x == 0) s_lwords = 0;
+    __syncthreads();
+    if (threadIdx.x < sd.n) {
+    const int g = sd.g0 + threadIdx.x;
+    const int cur = ctl->cur ^ 1, gen = ctl->gen ^ 1;  // the halves reorder just wrote
+    const double2* __restrict__ P = st.XY[cur];
+    const int* __restrict__ idv = st.ID[gen];
+    const int* __restrict__ start = st.cell_start + ctl->cell_base;
+    const int b = ctl->b;
+    const double L = ctl->L, Lh = ctl->Lover2, rs2 = st.rs2;
+    const double2 me = P[g];
+    const int c = st.BOX[gen][g];
+    const int cx = c / b, cy = c - cx * b;
+
+    double kd[MAX_S];
+    int kj[MAX_S];
+    int n = 0, total = 0;
+    const int S = st.S;
+
+    for (int dcx = -1; dcx <= 1; dcx++) {
+        int col = cx + dcx;
+        if (col < 0) col += b; else if (col >= b) col -= b;
+        // rows cy-1..cy+1 of this column: one run, or split where y wraps
+        int r0[3], r1[3], nr;
+        if (cy >= 1 && cy <= b - 2) {
+            r0[0] = start[col * b + cy - 1]; r1[0] = start[col * b + cy + 2]; nr = 1;
+        } else {
+            nr = 3;
+            for (int dcy = -1; dcy <= 1; dcy++) {
+                int row = cy + dcy;
+                if (row < 0) row += b; else if (row >= b) row -= b;
+                r0[dcy + 1] = start[col * b + row]; r1[dcy + 1] = start[col * b + row + 1];
+            }
+        }
+        for (int r = 0; r < nr; r++) {
+            for (int j = r0[r]; j < r1[r]; j++) {
+                if (j == g) continue;
+                const double2 pj = P[j];
+                const double dx = apj_wrap1(pj.x - me.x, L, Lh);
+                const double dy = apj_wrap1(pj.y - me.y, L, Lh);
+                const double d2 = apj_d2(dx, dy);
+                if (d2 < rs2) {
+                    total++;
+                    // insert into the list kept sorted by (d2, id)
+                    const int idj = idv[j];
+                    int q = n - 1;
+                    if (n == S) {   // full: drop the farthest (flagged as overflow below)
+                        if (!(d2 < kd[q] || (d2 == kd[q] && idj < idv[kj[q]]))) continue;
+                        q--;
+                    } else {
+                        n++;
+                    }
+                    while (q >= 0 && (kd[q] > d2 || (kd[q] == d2 && idv[kj[q]] > idj))) {
+                        kd[q + 1] = kd[q]; kj[q + 1] = kj[q]; q--;
+                    }
+                    kd[q + 1] = d2; kj[q + 1] = j;
+                }
+            }
+        }
+    }
+    // word w of this particle -> [w / G][p * G + w % G] of the block's [round][tb] array
+    const int G = st.G;
+    unsigned* __restrict__ out = st.list32 + bg * (long long)st.max_rounds * st.tb + threadIdx.x * G;
+    for (int k = 0; k < n; k += 2) {
+        const unsigned lo = (unsigned)apj_slot_of(sd, kj[k]) & 0xffffu;
+        const unsigned hi = (k + 1 < n) ? ((unsigned)apj_slot_of(sd, kj[k + 1]) & 0xffffu) : 0u;
+        const int w = k >> 1;
+        out[(w / G) * st.tb + (w % G)] = lo | (hi << 16);
+    }
+    st.cnt[g] = n;
+    if (total > S) ctl->overflow |= 1;
+    if (total > ctl->list_max) atomicMax(&ctl->list_max, total);
+    atomicMax(&s_lwords, (n + 1) / 2);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st.tiles[bg].info = sd.info | (s_lwords << 16);
+}
+
+__global__ void apj_finish_rebuild_kernel(const DevState st) {
+    const int sys = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sys >= st.n_sys) return;
+    SysCtl* ctl = st.ctl + sys;
+    if (!ctl->stale) return;
+    if (ctl->overflow & 2) return;   // tile larger than the launched shared-memory capacity: nothing was
+                                     // committed, the system stays stale until the host re-launches bigger
+    ctl->cur ^= 1;
+    ctl->gen ^= 1;
+    if (ctl->save_old) {   // newSkinList fired (jamming.cpp:611-615): resetCounter++, saveOldPositions
+        ctl->COM_old[0] = ctl->COM[0];
+        ctl->COM_old[1] = ctl->COM[1];
+        ctl->reset_counter += 1;
+    }
+    ctl->n_rebuilds += 1;
+    ctl->save_old = 0;
+    ctl->stale = 0;
+}
+
+}  // namespace
+
+void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nbox, int max_b) {
+    (void)max_b;
+    const int bps = (st.N + RB_BLOCK - 1) / RB_BLOCK;
+    const int grid = st.n_sys * bps;
+    apj_bin_count_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
+    apj_cell_scan_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st);
+    apj_scatter_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
+    dim3 gs((max_nbox + RB_BLOCK - 1) / RB_BLOCK, st.n_sys);
+    apj_cell_sort_kernel<<<gs, RB_BLOCK, 0, l.stream>>>(st);
+    apj_reorder_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
+    apj_make_tiles_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st);
+    apj_verlet_build_kernel<<<st.n_sys * st.maxblk, st.ppb, 0, l.stream>>>(st);
+    apj_finish_rebuild_kernel<<<(st.n_sys + 63) / 64, 64, 0, l.stream>>>(st);
+    if (l.launch_counter) (*l.launch_counter) += 8;
+}
+
+int apj_max_list_capacity() { return MAX_S; }

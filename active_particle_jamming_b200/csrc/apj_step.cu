@@ -1,0 +1,374 @@
+// Fused step kernel: one launch = one Engine::calculate_next_positions() (reference
+// code/jam/jamming.cpp:837-853) for every batched system, evaluated speculatively:
+//
+//   newSkinList (:587-617)          -> per-particle COM-corrected displacement, block top-2
+//   neighborInteractions (:623-669) -> gather sweep over the full Verlet list (no atomics,
+//                                      SURVEY Q18): soft-disk force + Vicsek sum, then
+//                                      phi = atan2 + CTnoise * U[-PI,PI)
+//   Cell::update (classes/Cell.h:92-118,157-175) -> wrap, sincos, propulsion, Euler, PBC
+//   calculate_COM (:761-774)        -> block partial sums of x_real
+//
+// Work decomposition. A block (TB = 128 or 256 threads) owns PPB = TB/G consecutive particles of one cell
+// column (TileDesc, built at every rebuild). Everything those particles can interact with
+// lives in <= 6 contiguous runs of the cell-ordered arrays (three columns x rows
+// cy0-1..cy1+1, split where y wraps). One thread issues TMA bulk copies (cp.async.bulk +
+// mbarrier) of those runs of {x,y}, {cos,sin}, {R,1/R} and of the block's list words into
+// shared memory: one memory round trip per block. The neighbour sweep runs out of shared
+// memory with G lanes per particle (G = 1 for large systems; G = 2/4/8 spreads a small system
+// over enough warps to hide latency), partial sums are combined with __shfl_xor and handed to
+// one thread per particle for the transcendental epilogue, which runs lane-dense. Lists are
+// distance-sorted, so the interacting partners come first and the force branch is coherent.
+//
+// Results go to the *other* half of the ping-pong buffers. The last block to finish reduces
+// the per-block partials in a fixed order (deterministic) and either COMMITS the step (flips
+// ctl.cur, advances ctl.step, stores COM) or, if the skin test of the state the step STARTED
+// from says the lists were too old, marks the system stale and leaves the state untouched: the
+// rebuild chain then re-bins from the intact input buffers and the step is re-run. The rebuild
+// decision therefore falls on exactly the step the reference takes it on, with no host round
+// trip and no extra pass over the particles.
+#include "apj_device.cuh"
+
+namespace {
+
+struct PairAcc { double Fx, Fy, ax, ay; };
+
+// one neighbour: reference jamming.cpp:633-662 seen from particle i (gather form)
+template <bool WRAP>
+__device__ __forceinline__ void pair_term(PairAcc& a, const double2 me, const double Ri, const unsigned slot,
+                                          const double2* __restrict__ sXY, const double2* __restrict__ sCS,
+                                          const double2* __restrict__ sRR, const double L, const double Lh, const double rn2) {
+    const double2 q = sXY[slot];
+    double dx = q.x - me.x, dy = q.y - me.y;
+    if (WRAP) { dx = apj_wrap1(dx, L, Lh); dy = apj_wrap1(dy, L, Lh); }   // delta_norm (:872-880)
+    const double d2 = apj_d2(dx, dy);
+    if (d2 < rn2) {                                   // they're neighbours (:637)
+        const double sumR = Ri + sRR[slot].x;
+        if (d2 < sumR * sumR) {                       // they also overlap (:641)
+            // overlap = sumR / sqrt(d2) - 1 (:643), evaluated as sumR * rsqrt(d2) - 1: rsqrt is
+            // correct to 1 ulp, so the quotient differs from the reference's by <= ~2 ulp
+            // (4e-16), far inside the 1e-12 gate, at a third of the instruction count.
+            const double overlap = sumR * rsqrt(d2) - 1;
+            a.Fx -= overlap * dx;
+            a.Fy -= overlap * dy;
+        }
+        const double2 cs = sCS[slot];
+        a.ax += cs.x;                                 // add up orientations of neighbours (:659-660)
+        a.ay += cs.y;
+    }
+}
+
+template <int TB, int G, bool WRAP>
+__device__ __forceinline__ void sweep(PairAcc& acc, const int rounds, const int srounds, const int n, const int sub,
+                                      const unsigned* __restrict__ sL, const unsigned* __restrict__ gL,
+                                      const double2 me, const double Ri, const double2* __restrict__ sXY,
+                                      const double2* __restrict__ sCS, const double2* __restrict__ sRR,
+                                      const double L, const double Lh, const double rn2) {
+#pragma unroll 2
+    for (int i = 0; i < srounds; i++) {               // rows staged in shared memory
+        const unsigned word = sL[i * TB + threadIdx.x];
+        const int k0 = 2 * (sub + G * i);
+        if (k0 < n) pair_term<WRAP>(acc, me, Ri, word & 0xffffu, sXY, sCS, sRR, L, Lh, rn2);
+        if (k0 + 1 < n) pair_term<WRAP>(acc, me, Ri, word >> 16, sXY, sCS, sRR, L, Lh, rn2);
+    }
+    for (int i = srounds; i < rounds; i++) {          // rare: lists longer than the staged rows
+        const int k0 = 2 * (sub + G * i);
+        if (k0 < n) {
+            const unsigned word = __ldg(gL + i * TB + threadIdx.x);
+            pair_term<WRAP>(acc, me, Ri, word & 0xffffu, sXY, sCS, sRR, L, Lh, rn2);
+            if (k0 + 1 < n) pair_term<WRAP>(acc, me, Ri, word >> 16, sXY, sCS, sRR, L, Lh, rn2);
+        }
+    }
+}
+
+template <int TB, int G, bool INJECT>
+__global__ void __launch_bounds__(TB, (TB == 256 ? 4 : 8))
+apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const int always_full) {
+    constexpr int PPB = TB / G;                        // particles per block
+    constexpr int EWARPS = (PPB + 31) / 32;            // warps that run the epilogue
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ TileDesc sd;
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ double4 s_red[EWARPS];
+
+    const int sys = blockIdx.x / st.maxblk;
+    const int blk = blockIdx.x - sys * st.maxblk;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const long long bg = (long long)sys * st.maxblk + blk;
+    int desc_word = 0;                                 // fetched alongside ctl: one round trip, not two
+    if (t < 16) desc_word = __ldg(reinterpret_cast<const int*>(st.tiles + bg) + t);
+    SysCtl* __restrict__ ctl = st.ctl + sys;
+    const int nblk = ctl->nblk;
+    const long long step = ctl->step;
+    if (blk >= nblk || ctl->stale || step >= ctl->target) return;  // uniform over the system's blocks
+
+    const int cur = ctl->cur, gen = ctl->gen;
+
+    double2* __restrict__ sXY = reinterpret_cast<double2*>(smem_raw);
+    double2* __restrict__ sCS = sXY + st.tile_cap;
+    double2* __restrict__ sRR = sCS + st.tile_cap;
+    unsigned* __restrict__ sL = reinterpret_cast<unsigned*>(sRR + st.tile_cap);
+    double4* __restrict__ sAcc = reinterpret_cast<double4*>(sL + st.smem_rounds * TB);
+
+    if (t < 16) reinterpret_cast<int*>(&sd)[t] = desc_word;
+    if (t == 0) apj_mbar_init(&s_bar, 1);
+    __syncthreads();
+
+    const int npieces = sd.info & 0xff;
+    const bool wraps = (sd.info >> 8) & 1;
+    const int lwords = sd.info >> 16;
+    const int rounds = (lwords + G - 1) / G;
+    const int srounds = min(rounds, st.smem_rounds);
+    const unsigned* __restrict__ gL = st.list32 + bg * (long long)st.max_rounds * TB;
+
+    if (t == 0) {   // stage the tile (<= 6 pieces x 3 arrays of 16 B elements) and the list words
+        int slots = 0;
+        for (int p = 0; p < npieces; p++) slots += sd.plen[p];
+        apj_mbar_expect_tx(&s_bar, (unsigned)slots * 48u + (unsigned)srounds * (TB * 4u));
+        int off = 0;
+        for (int p = 0; p < npieces; p++) {
+            const unsigned bytes = (unsigned)sd.plen[p] * 16u;
+            apj_bulk_g2s(sXY + off, st.XY[cur] + sd.pstart[p], bytes, &s_bar);
+            apj_bulk_g2s(sCS + off, st.CS[cur] + sd.pstart[p], bytes, &s_bar);
+            apj_bulk_g2s(sRR + off, st.RR[gen] + sd.pstart[p], bytes, &s_bar);
+            off += sd.plen[p];
+        }
+        if (srounds) apj_bulk_g2s(sL, gL, (unsigned)srounds * (TB * 4u), &s_bar);
+    }
+
+    // per-thread loads that do not depend on the tile: in flight while the TMA copies land
+    const int p = t / G, sub = t - p * G;              // sweep mapping: G adjacent lanes per particle
+    const bool sweeping = p < sd.n;
+    const int n = sweeping ? st.cnt[sd.g0 + p] : 0;
+    const bool active = t < sd.n;                      // epilogue mapping: thread t <-> particle t
+    const long long g = (long long)sd.g0 + (active ? t : 0);
+    double2 xo = make_double2(0.0, 0.0), xr = xo;
+    int id = 0;
+    if (t < PPB) { xo = st.XO[gen][g]; xr = st.XR[cur][g]; id = st.ID[gen][g]; }
+    const double L = ctl->L, Lh = ctl->Lover2;
+    const double rn2 = st.rn2;
+
+    apj_mbar_wait(&s_bar, 0);
+
+    // ---- neighborInteractions ----
+    PairAcc acc = {0.0, 0.0, 0.0, 0.0};
+    {
+        const int own = sd.own_slot + (sweeping ? p : 0);
+        const double2 me = sXY[own];
+        const double Ri = sRR[own].x;
+        if (wraps) sweep<TB, G, true>(acc, rounds, srounds, n, sub, sL, gL, me, Ri, sXY, sCS, sRR, L, Lh, rn2);
+        else sweep<TB, G, false>(acc, rounds, srounds, n, sub, sL, gL, me, Ri, sXY, sCS, sRR, L, Lh, rn2);
+    }
+    if (G > 1) {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            acc.Fx += __shfl_xor_sync(0xffffffffu, acc.Fx, o);
+            acc.Fy += __shfl_xor_sync(0xffffffffu, acc.Fy, o);
+            acc.ax += __shfl_xor_sync(0xffffffffu, acc.ax, o);
+            acc.ay += __shfl_xor_sync(0xffffffffu, acc.ay, o);
+        }
+        if (sub == 0) sAcc[p] = make_double4(acc.Fx, acc.Fy, acc.ax, acc.ay);
+        __syncthreads();
+        if (wid >= EWARPS) return;                     // only the epilogue warps continue
+        const double4 a = sAcc[t < PPB ? t : 0];
+        acc.Fx = a.x; acc.Fy = a.y; acc.ax = a.z; acc.ay = a.w;
+    }
+
+    double sum_x = 0.0, sum_y = 0.0, top1 = 0.0, top2 = 0.0;
+    if (active) {
+        const int own = sd.own_slot + t;
+        const double2 me = sXY[own], mcs = sCS[own], mrr = sRR[own];
+        const double Ri = mrr.x;
+        double Fx = acc.Fx, Fy = acc.Fy, ax = acc.ax, ay = acc.ay;
+        if (!ctl->no_self_once) { ax += mcs.x; ay += mcs.y; }  // self term: Cell::update left x_new = cosp (Cell.h:102-103)
+
+        // ---- newSkinList: displacement since the last rebuild, COM drift removed ----
+        {
+            const double ddx = apj_delta_norm(((me.x - xo.x) - ctl->COM[0]) + ctl->COM_old[0], L, Lh);
+            const double ddy = apj_delta_norm(((me.y - xo.y) - ctl->COM[1]) + ctl->COM_old[1], L, Lh);
+            top1 = apj_d2(ddx, ddy);
+        }
+
+        // ---- phi = atan2(y_new, x_new) + CTnoise * randuni()   (jamming.cpp:667) ----
+        double u;
+        if (INJECT) {
+            u = noise_by_id[(long long)sys * st.N + id];
+        } else {
+            const unsigned w = apj_philox_word0((unsigned)id, (unsigned)step, (unsigned)(step >> 32), (unsigned)sys,
+                                                (unsigned)st.seed, (unsigned)(st.seed >> 32));
+            u = apj_u32_to_randuni(w);
+        }
+        double phi = atan2(ay, ax) + ctl->CTnoise * u;
+
+        // ---- Cell::update ----
+        if (phi >= APJ_PI) phi -= APJ_PI2;            // periodicAngles, single wrap (Cell.h:160-166)
+        else if (phi < -APJ_PI) phi += APJ_PI2;
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        double CF = ctl->CFself;
+        if (ctl->ramp_len > 0) {                      // relax() ramp (jamming.cpp:518)
+            const long long t_ = step - ctl->ramp_t0;
+            if (t_ < ctl->ramp_len) CF = CF - (double)(ctl->ramp_len - t_) * CF / (double)ctl->ramp_len;
+        }
+        Fx += cs * CF * Ri;
+        Fy += sn * CF * Ri;
+        const double vx = Fx * mrr.y, vy = Fy * mrr.y;   // Rinv = 1/R stored at upload (jamming.cpp:298)
+        const double dx = vx * st.dt, dy = vy * st.dt;
+        double x = me.x + dx, y = me.y + dy;
+        const double xrn = xr.x + dx, yrn = xr.y + dy;
+        if (x >= Lh) x -= L; else if (x < -Lh) x += L;   // Cell::PBC, single wrap (Cell.h:168-175)
+        if (y >= Lh) y -= L; else if (y < -Lh) y += L;
+
+        st.XY[cur ^ 1][g] = make_double2(x, y);
+        st.CS[cur ^ 1][g] = make_double2(cs, sn);
+        st.XR[cur ^ 1][g] = make_double2(xrn, yrn);
+        if (always_full || step + 1 == ctl->target) {   // fields only observables read
+            st.V[gen][g] = make_double2(vx, vy);
+            st.PHI[gen][g] = phi;
+        }
+        sum_x = xrn; sum_y = yrn;
+    }
+
+    // ---- block reduction: sum of x_real, top-2 displacement^2 ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum_x += __shfl_xor_sync(0xffffffffu, sum_x, o);
+        sum_y += __shfl_xor_sync(0xffffffffu, sum_y, o);
+        const double b1 = __shfl_xor_sync(0xffffffffu, top1, o), b2 = __shfl_xor_sync(0xffffffffu, top2, o);
+        apj_top2_merge(top1, top2, b1, b2);
+    }
+    if (EWARPS > 1) {
+        if (lane == 0) s_red[wid] = make_double4(sum_x, sum_y, top1, top2);
+        __syncthreads();       // all EWARPS == all warps of the block when EWARPS > 1 (G == 1 or 2)
+        if (wid != 0) return;
+#pragma unroll
+        for (int w = 1; w < EWARPS; w++) {
+            const double4 b = s_red[w];
+            sum_x += b.x; sum_y += b.y;
+            apj_top2_merge(top1, top2, b.z, b.w);
+        }
+    }
+    // warp 0 only from here. Two-level, fixed-order reduction of the per-block partials: the last
+    // block of each group of 32 folds its group, the last group to finish folds the groups and
+    // commits. Deterministic (membership and order are fixed) and O(sqrt)-deep in the tail.
+    const int grp = blk >> 5, ngrp = (nblk + 31) >> 5;
+    const int gsize = min(32, nblk - (grp << 5));
+    unsigned* __restrict__ gticket = st.gticket + (long long)sys * st.maxgrp;
+    double4* __restrict__ gpart = st.gpartials + (long long)sys * st.maxgrp;
+    unsigned last = 0;
+    if (lane == 0) {
+        st.partials[bg] = make_double4(sum_x, sum_y, top1, top2);
+        __threadfence();
+        last = (atomicAdd(gticket + grp, 1u) == (unsigned)gsize - 1u) ? 1u : 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    double4 a = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (lane < gsize) {
+        const double4* q = st.partials + (long long)sys * st.maxblk + (grp << 5) + lane;
+        const double2 b01 = __ldcg(reinterpret_cast<const double2*>(q));
+        const double2 b23 = __ldcg(reinterpret_cast<const double2*>(q) + 1);
+        a = make_double4(b01.x, b01.y, b23.x, b23.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+        const double b1 = __shfl_xor_sync(0xffffffffu, a.z, o), b2 = __shfl_xor_sync(0xffffffffu, a.w, o);
+        apj_top2_merge(a.z, a.w, b1, b2);
+    }
+    last = 0;
+    if (lane == 0) {
+        gticket[grp] = 0u;
+        gpart[grp] = a;
+        __threadfence();
+        last = (atomicAdd(&ctl->ticket, 1u) == (unsigned)ngrp - 1u) ? 1u : 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+
+    // ---- last group of this system: fold the group partials, then commit ----
+    __threadfence();
+    a = make_double4(0.0, 0.0, 0.0, 0.0);
+    for (int k0 = 0; k0 < ngrp; k0 += 32 * 8) {
+        double2 v01[8], v23[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {                  // 8 independent loads in flight per lane
+            const int k = k0 + u * 32 + lane;
+            v01[u] = make_double2(0.0, 0.0); v23[u] = make_double2(0.0, 0.0);
+            if (k < ngrp) {
+                v01[u] = __ldcg(reinterpret_cast<const double2*>(gpart + k));
+                v23[u] = __ldcg(reinterpret_cast<const double2*>(gpart + k) + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a.x += v01[u].x; a.y += v01[u].y;
+            apj_top2_merge(a.z, a.w, v23[u].x, v23[u].y);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+        const double b1 = __shfl_xor_sync(0xffffffffu, a.z, o), b2 = __shfl_xor_sync(0xffffffffu, a.w, o);
+        apj_top2_merge(a.z, a.w, b1, b2);
+    }
+    if (lane == 0) {
+        ctl->ticket = 0u;
+        if (sqrt(a.z) + sqrt(a.w) > st.skin) {   // jamming.cpp:611
+            ctl->stale = 1;                      // lists too old for the state this step read:
+            ctl->save_old = 1;                   // drop the speculative result, rebuild, re-run
+            ctl->n_discarded += 1;
+        } else {
+            ctl->COM[0] = a.x / st.N;            // calculate_COM (jamming.cpp:761-774)
+            ctl->COM[1] = a.y / st.N;
+            ctl->cur = cur ^ 1;
+            ctl->step = step + 1;
+            ctl->no_self_once = 0;
+        }
+    }
+}
+
+size_t step_smem_bytes(const DevState& st) {
+    return (size_t)st.tile_cap * 48 + (size_t)st.smem_rounds * st.tb * 4 + (size_t)st.ppb * 32;
+}
+
+template <int TB, int G>
+int configure(const DevState& st) {
+    const int bytes = (int)step_smem_bytes(st);
+    if (cudaFuncSetAttribute(apj_step_kernel<TB, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(apj_step_kernel<TB, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+    return 0;
+}
+
+template <int TB, int G>
+void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int always_full) {
+    const int grid = st.n_sys * st.maxblk;
+    const size_t smem = step_smem_bytes(st);
+    if (noise_by_id) apj_step_kernel<TB, G, true><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
+    else apj_step_kernel<TB, G, false><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+}
+
+}  // namespace
+
+#define APJ_DISPATCH(CALL)                                                   \
+    if (st.tb == 256 && st.G == 1) { CALL(256, 1); }                         \
+    else if (st.tb == 128 && st.G == 1) { CALL(128, 1); }                    \
+    else if (st.tb == 128 && st.G == 2) { CALL(128, 2); }                    \
+    else if (st.tb == 128 && st.G == 4) { CALL(128, 4); }                    \
+    else if (st.tb == 128 && st.G == 8) { CALL(128, 8); }
+
+int apj_configure_kernels(const DevState& st) {
+#define APJ_CFG(TB, G) return configure<TB, G>(st)
+    APJ_DISPATCH(APJ_CFG)
+#undef APJ_CFG
+    return -1;
+}
+
+void apj_launch_step(const DevState& st, const ApjLaunch& l, const double* noise_by_id, int always_full) {
+#define APJ_LAUNCH(TB, G) launch<TB, G>(st, l.stream, noise_by_id, always_full)
+    APJ_DISPATCH(APJ_LAUNCH)
+#undef APJ_LAUNCH
+    if (l.launch_counter) (*l.launch_counter)++;
+}

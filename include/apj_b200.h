@@ -1,0 +1,158 @@
+/* apj_b200.h -- C ABI of the B200-native active-particle-jamming hot path.
+ *
+ * The reference (danielmccusker/active-particle-jamming) has no FFI layer: its hot path is a set
+ * of `Engine` methods in one translation unit (code/jam/jamming.cpp) over header-only structs
+ * (code/classes/*.h). This header is the boundary a host `Engine` binds instead of those
+ * methods; every entry point names the reference code it replaces (file:line relative to the
+ * reference root). INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions: plain C, no exceptions; every function returns 0 on success or a negative
+ * APJ_E_* code, with a human-readable message from apj_last_error(); all device memory is owned
+ * by the handle; all buffers passed in are caller-owned HOST memory laid out one value per
+ * particle in ORIGINAL PARTICLE INDEX order, system-major (index = system * N + id); one CUDA
+ * stream per handle; calls on one handle must come from one host thread. There is NO CPU
+ * fallback: without a usable CUDA device apj_create fails with APJ_E_CUDA.
+ */
+#ifndef APJ_B200_H
+#define APJ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APJ_OK 0
+#define APJ_E_INVALID (-1)  /* bad argument */
+#define APJ_E_CUDA (-2)     /* CUDA runtime / driver error (message has the CUDA string) */
+#define APJ_E_OVERFLOW (-3) /* a Verlet list exceeded max_neighbors; recreate with a larger value */
+#define APJ_E_STATE (-4)    /* call not valid in the current state (e.g. no state uploaded) */
+#define APJ_E_NCCL (-5)     /* NCCL error (slab mode) */
+
+typedef struct apj_engine apj_engine;
+
+/* Engine::Engine + the constants it fixes (jamming.cpp:57, :112-115, :119-165). */
+typedef struct apj_config {
+    int64_t n;             /* particles per system (Engine::N) */
+    int32_t n_systems;     /* independent replicas batched in one handle (phase-diagram sweep); >= 1 */
+    int32_t device;        /* CUDA device ordinal */
+    double dt;             /* 0 -> 0.1  (jamming.cpp:57) */
+    double rn;             /* 0 -> 2.8  (jamming.cpp:112) */
+    double rs_factor;      /* 0 -> 1.5  (rs = 1.5*rn, jamming.cpp:113) */
+    uint64_t seed;         /* Philox4x32-10 key */
+    int32_t max_neighbors; /* capacity of one full Verlet list; 0 -> 48 */
+    int32_t steps_per_launch; /* speculative steps between rebuild checks; 0 -> 16 */
+    int32_t flags;         /* APJ_FLAG_* */
+    int32_t tile_slots;    /* shared-memory tile capacity of a work block, in particles; 0 -> adaptive (follows the largest tile) */
+    int32_t lanes_per_particle; /* threads cooperating on one neighbour sweep: 1, 2, 4, 8; 0 -> by system size */
+    int32_t reserved;
+} apj_config;
+
+#define APJ_FLAG_NO_GRAPH 1  /* launch kernels directly instead of through a CUDA graph */
+
+/* Host view of the per-particle fields of `struct Cell` (classes/Cell.h:15-43), 2D. Any
+ * pointer may be NULL: on upload a NULL field takes the documented default, on download it is
+ * skipped. */
+typedef struct apj_state {
+    double *x, *y;           /* Cell::x          */
+    double *x_real, *y_real; /* Cell::x_real     (upload default: x, y) */
+    double *x0, *y0;         /* Cell::x0         (upload default: x_real) */
+    double *x_old, *y_old;   /* Cell::x_old      (upload default: x, y) */
+    double *R;               /* Cell::R          (Rinv = 1/R is derived, jamming.cpp:298) */
+    double *phi;             /* Cell::phi */
+    double *cosp, *sinp;     /* Cell::cosp/sinp  (upload default: cos(phi), sin(phi), jamming.cpp:332-333) */
+    double *vx, *vy;         /* Cell::vx, vy     (upload default: 0) */
+    int32_t *box;            /* Cell::box, reference numbering i + j*b (upload default: -1) */
+} apj_state;
+
+const char* apj_version(void);
+const char* apj_last_error(const apj_engine* e); /* e may be NULL: message of the failed apj_create */
+
+/* Engine::Engine + Engine::topology scalars (jamming.cpp:119, :361-365): L[s] is the box length
+ * of system s; b = floor(L/(2 rn)), lp = L/b, nbox = b*b are derived exactly as the reference. */
+int apj_create(const apj_config* cfg, const double* L, apj_engine** out);
+int apj_destroy(apj_engine* e);
+
+/* lambda_s / lambda_n per system (Engine::CFself, Engine::CTnoise; jamming.cpp:49-50). */
+int apj_set_activity(apj_engine* e, const double* CFself, const double* CTnoise);
+/* relax() thermalisation ramp (jamming.cpp:516-520): for the next calls of apj_step, step k
+ * (k = 0.. from now) runs with CFself = CFself_final - (tthermalize - k)*CFself_final/tthermalize
+ * while k < tthermalize, then CFself_final. tthermalize = 0 cancels the ramp. */
+int apj_set_ramp(apj_engine* e, int64_t tthermalize);
+
+/* Replaces the state that initCells builds in vector<Cell> (jamming.cpp:285-354). Computes COM
+ * from x_real in index order (calculate_COM, :761-774), sets COM_old = COM0 = COM unless
+ * apj_set_com is called afterwards, then bins and builds the lists (assignCellsToGrid +
+ * buildVerletLists, start() :184-185) WITHOUT touching x_old. */
+int apj_upload_state(apj_engine* e, const apj_state* host);
+int apj_download_state(apj_engine* e, apj_state* host);
+/* COM / COM0 / COM_old of one system (jamming.cpp:89-91); NULL pointers are skipped. */
+int apj_set_com(apj_engine* e, int32_t system, const double* com, const double* com0, const double* com_old);
+int apj_get_com(apj_engine* e, int32_t system, double* com, double* com0, double* com_old);
+/* start() :191-203: x_real = x0 = x, COM, COM0 = COM, saveOldPositions(). */
+int apj_mark_origin(apj_engine* e);
+/* The reference's very first step has no self term in the alignment sum (Cell::x_new is 0
+ * until the first Cell::update, classes/Cell.h:75,102). 1 = drop the self term for the next
+ * committed step only. */
+int apj_skip_self_term_once(apj_engine* e, int32_t on);
+
+/* n x Engine::calculate_next_positions (jamming.cpp:837-853): skin test (newSkinList :587-617),
+ * on-device rebuild when it fires (assignCellsToGrid :527-548, buildVerletLists :550-585,
+ * saveOldPositions :825-835), fused pair sweep (neighborInteractions :623-669) + Cell::update
+ * (classes/Cell.h:92-118,157-175) + calculate_COM (:761-774). Noise: Philox4x32-10, counter =
+ * (particle id, step), key = seed, mapped like boost::uniform_real on mt19937 (u/2^32*2PI-PI). */
+int apj_step(apj_engine* e, int64_t n_steps);
+/* One step in which randuni() for particle id of system s returns noise[s*N + id]
+ * (replaces the RNG draw at jamming.cpp:667; parity gate). */
+int apj_step_injected(apj_engine* e, const double* noise);
+/* assignCellsToGrid + buildVerletLists without the skin bookkeeping (start() :184-185, :245-246). */
+int apj_force_rebuild(apj_engine* e);
+int apj_sync(apj_engine* e);
+
+/* out[8] = {step index, resetCounter (jamming.cpp:64), rebuilds incl. forced, longest list,
+ *           overflow flag, kernel launches so far, discarded speculative steps, b*b} */
+int apj_get_counters(apj_engine* e, int32_t system, int64_t* out8);
+int apj_set_reset_counter(apj_engine* e, int32_t system, int64_t value); /* relax() :524 */
+/* out[8] = {lanes per particle, threads per block, particles per block, tile capacity (slots),
+ *           largest tile in use, dynamic shared memory per block (bytes), work blocks, steps per launch} */
+int apj_get_tuning(apj_engine* e, int32_t* out8);
+/* out[5] = {L, Lover2, lp, b, nbox}  (jamming.cpp:99-103) */
+int apj_get_geometry(apj_engine* e, int32_t system, double* out5);
+
+/* Neighbour pair set of one system as a half list by particle id (the parity object of
+ * SURVEY Q1): offsets[N+1], idx[cap] (partners j > i, ascending). *total receives the pair
+ * count; idx may be NULL to query it. Replaces reading Cell::VerletList. */
+int apj_get_pair_list(apj_engine* e, int32_t system, int64_t* offsets, int32_t* idx, int64_t cap, int64_t* total);
+/* Box::CellList of every box (classes/Box.h:13), reference box numbering, ascending particle id:
+ * offsets[nbox+1], idx[N]. */
+int apj_get_cell_lists(apj_engine* e, int32_t system, int64_t* offsets, int32_t* idx);
+
+/* ---- observables (per system: out arrays have n_systems entries / rows) ---- */
+/* calculateOrderParameter + calculateSystemOrientation (jamming.cpp:776-806): order[s],
+ * orient[2*s..]. */
+int apj_order_orientation(apj_engine* e, double* order, double* orient);
+/* Engine::MSD (jamming.cpp:808-823). */
+int apj_msd(apj_engine* e, double* msd);
+/* Inner loop of Fluctuations::measureFluctuations (classes/Fluctuations.h:62-76): total lens
+ * area between every disk and a circle of radius[s] centred on COM. */
+int apj_fluct_area(apj_engine* e, const double* radius, double* area);
+/* Correlations::spatialCorrelations raw sums (classes/Correlations.h:71-152) for one call:
+ * counts[nc], ori_sum[nc], vel_sum[nc], pair_sum[np] per system (rows of nc / np), with
+ * nc = ceil(cutoff/2.0), np = ceil(cutoff/0.1). Normalisation (:154-166) is left to the host. */
+int apj_spatial_correlations(apj_engine* e, double cutoff, double* counts, double* ori_sum, double* vel_sum, double* pair_sum);
+/* Correlations::velDist (classes/Correlations.h:179-187): counts per speed bin floor(v/dv[s]), 100 bins. */
+int apj_vel_hist(apj_engine* e, const double* dv, int64_t* hist100);
+/* Fluctuations::density_distribution (classes/Fluctuations.h:122-139): boxes per occupancy, 50 bins. */
+int apj_occupancy_hist(apj_engine* e, int64_t* hist50);
+
+/* CUDA-event timing on the handle's stream (bench.py; torch events cannot see this stream). */
+int apj_timer_begin(apj_engine* e);
+int apj_timer_end(apj_engine* e, float* milliseconds);
+/* Per-kernel timing of the fused step kernel: launches n single steps with an event pair around
+ * each step-kernel launch and returns the mean duration (ms) of those that committed. */
+int apj_time_step_kernel(apj_engine* e, int64_t n, float* mean_ms, int64_t* committed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APJ_B200_H */
