@@ -548,6 +548,37 @@ extern "C" int apj_get_geometry(apj_engine* e, int32_t s, double* o) {
     return APJ_OK;
 }
 
+__global__ void apj_list_stats_kernel(const int* __restrict__ cnt, long long n, unsigned long long* __restrict__ out) {
+    unsigned long long a = 0;
+    int mx = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = cnt[i];
+        a += (unsigned long long)c;
+        mx = max(mx, c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, a); atomicMax(out + 1, (unsigned long long)mx); }
+}
+
+extern "C" int apj_list_stats(apj_engine* e, int32_t s, int64_t* out2) {
+    if (!e || !out2 || s < 0 || s >= e->st.n_sys) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_list_stats: no state uploaded");
+    DevState& st = e->st;
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(e->obs.d_hist);
+    APJ_CUDA(e, cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), e->stream));
+    apj_list_stats_kernel<<<296, 256, 0, e->stream>>>(st.cnt + (long long)s * st.N, st.N, d);
+    e->launches++;
+    unsigned long long h[2];
+    APJ_CUDA(e, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    out2[0] = (int64_t)h[0]; out2[1] = (int64_t)h[1];
+    return APJ_OK;
+}
+
 extern "C" int apj_get_pair_list(apj_engine* e, int32_t s, int64_t* offsets, int32_t* idx, int64_t cap, int64_t* total) {
     if (!e || s < 0 || s >= e->st.n_sys || !total) return APJ_E_INVALID;
     if (!e->have_state) return fail(e, APJ_E_STATE, "apj_get_pair_list: no state uploaded");

@@ -43,7 +43,7 @@ class _State(C.Structure):
 EXPORTS = ["apj_version", "apj_last_error", "apj_create", "apj_destroy", "apj_set_activity", "apj_set_ramp",
            "apj_upload_state", "apj_download_state", "apj_set_com", "apj_get_com", "apj_mark_origin",
            "apj_skip_self_term_once", "apj_step", "apj_step_injected", "apj_force_rebuild", "apj_sync",
-           "apj_get_counters", "apj_get_tuning", "apj_set_reset_counter", "apj_get_geometry", "apj_get_pair_list", "apj_get_cell_lists",
+           "apj_get_counters", "apj_get_tuning", "apj_set_reset_counter", "apj_get_geometry", "apj_get_pair_list", "apj_get_cell_lists", "apj_list_stats",
            "apj_order_orientation", "apj_msd", "apj_fluct_area", "apj_spatial_correlations", "apj_vel_hist",
            "apj_occupancy_hist", "apj_timer_begin", "apj_timer_end", "apj_time_step_kernel"]
 
@@ -82,6 +82,7 @@ def load_library():
     L.apj_get_geometry.argtypes = [C.c_void_p, C.c_int32, _dp]
     L.apj_get_pair_list.argtypes = [C.c_void_p, C.c_int32, _lp, _ip, C.c_int64, _lp]
     L.apj_get_cell_lists.argtypes = [C.c_void_p, C.c_int32, _lp, _ip]
+    L.apj_list_stats.argtypes = [C.c_void_p, C.c_int32, _lp]
     L.apj_order_orientation.argtypes = [C.c_void_p, _dp, _dp]
     L.apj_msd.argtypes = [C.c_void_p, _dp]
     L.apj_fluct_area.argtypes = [C.c_void_p, _dp, _dp]
@@ -248,6 +249,12 @@ class DeviceEngine:
         off, idx = self.pair_list(system)
         i = np.repeat(np.arange(self.n, dtype=np.int64), np.diff(off))
         return np.stack([i, idx.astype(np.int64)], axis=1)
+
+    def list_stats(self, system=0):
+        """(mean full-list length n_full, longest list) of the lists currently held."""
+        o = np.zeros(2, dtype=np.int64)
+        self._chk(self.lib.apj_list_stats(self.h, int(system), _p(o, _lp)))
+        return o[0] / self.n, int(o[1])
 
     def cell_lists(self, system=0):
         nbox = self.geometry(system)["nbox"]

@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 hot path: fp64 particle-steps/s of Engine::calculate_next_positions
+(reference code/jam/jamming.cpp:837-853) through the C ABI of include/apj_b200.h.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code on the host cores
+
+One bench step = ONE Euler step of every particle of the workload (one call of
+calculate_next_positions); `value` = particles x K / time of the K timed steps, state resident in
+HBM (CUDA events on the engine's stream, max over ranks); `e2e` = the same metric for a whole job
+through the host-facing API with HOST buffers: upload of the full state, the K steps with the
+reference driver's observable read-backs, download of the full state -- copies inside the timed
+region. Workloads (BASELINE.json configs): see WORKLOADS. One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PI = 3.14159265  # reference jamming.cpp:3
+
+WORKLOADS = {
+    # name: (particles, packing fraction, lambda_s, lambda_n, replicas, BASELINE.json config it is)
+    "box16m": (16777216, 0.9, 0.05, 0.5, 1, "configs[3]: N=16M periodic box (the configuration the 1e10 target is quoted on); slabs along x when n_gpus > 1"),
+    "jam65k": (65536, 1.0, 0.05, 0.5, 1, "configs[1]: N=65,536 above jamming, single B200"),
+    "obs1m": (1048576, 0.9, 0.05, 0.5, 1, "configs[2]: N=1M single B200"),
+    "sweep512": (4096, 0.9, 0.05, 0.5, 64, "configs[4]: 64 replicas x N=4096 per GPU"),
+}
+CPU_SAMPLE_N = 16384      # particles of one reference Engine in the CPU legs
+RELAX = (2000, 2000)      # trelax, tthermalize of the reference's local relax() (jamming.cpp:489-499)
+
+
+def synthetic_state(n, rho, seed):
+    """radii 1 + N(0,1)/10 (jamming.cpp:296), L = sqrt(PI sum R^2 / rho) (:305) summed
+    in index order, uniform random positions and angles."""
+    rng = np.random.default_rng(seed)
+    R = 1.0 + 0.1 * rng.standard_normal(n)
+    L = float(np.sqrt(PI * np.cumsum(R * R)[-1] / rho))    # cumsum = index-order accumulation, like the reference loop
+    x = rng.uniform(-L / 2, L / 2, n)
+    y = rng.uniform(-L / 2, L / 2, n)
+    phi = rng.uniform(-PI, PI, n)
+    return R, L, x, y, phi
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], 0.0, set()
+        for r in rows:
+            f = [c.strip() for c in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs: the reference's own code (oracle/_ref) on the host cores, one serial Engine per core --
+# the reference's parallel model is a job array of single-core runs (code/jam/jamming.sh:2-4).
+def cpu_worker(n, rho, l_s, l_n, seed, warm, steps):
+    from oracle import pyoracle
+    if pyoracle.have_ref():
+        E = pyoracle.RefEngine
+        E.seed(seed)
+        r = E(n, 1000, l_s, l_n, rho)
+        r.init_cells(); r.topology(); r.assign(); r.build()      # reference lattice init (jamming.cpp:285-354)
+        r.set_params(0.0, l_n); r.steps(warm // 2)
+        r.set_params(l_s, l_n); r.steps(warm - warm // 2)
+        r.mark_origin()
+        secs = r.time_steps(steps)
+        kind = "reference"
+    else:                                                            # reference build absent: the oracle port
+        R, L, x, y, phi = synthetic_state(n, rho, seed)
+        o = pyoracle.OracleSim.from_arrays(R, x, y, phi, rho)
+        o.topology(); o.assign(); o.build(); o.mark_origin()
+        o.set_params(0.0, l_n); o.run_philox(seed, 0, warm // 2)
+        o.set_params(l_s, l_n); o.run_philox(seed, warm // 2, warm - warm // 2)
+        t0 = time.perf_counter(); o.run_philox(seed, warm, steps); secs = time.perf_counter() - t0
+        kind = "port"
+    print(json.dumps({"secs": secs, "kind": kind}))
+
+
+def run_cpu(rho, l_s, l_n, warm, steps, n=CPU_SAMPLE_N):
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--_cpu_worker", json.dumps([n, rho, l_s, l_n, 1000 + k, warm, steps])],
+                              stdout=subprocess.PIPE, text=True, cwd=ROOT) for k in range(cores)]
+    outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in procs]
+    rate = sum(n * steps / o["secs"] for o in outs)
+    slowest = max(o["secs"] for o in outs)
+    return {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": outs[0]["kind"],
+            "sample": "%d independent serial Engines (one per host core, the reference's job-array model), N=%d each at phi=%g "
+                      "lambda_s=%g lambda_n=%g, reference lattice init + %d warm-up steps, %d timed calculate_next_positions() each"
+                      % (cores, n, rho, l_s, l_n, warm, steps),
+            "per_core": rate / cores, "secs": slowest}
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="box16m", choices=sorted(WORKLOADS))
+    ap.add_argument("--particles", type=int, default=0, help="override the workload's particle count")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-relax", action="store_true", help="shorten the relax() schedule (profiling runs)")
+    ap.add_argument("--_cpu_worker", default=None)
+    a = ap.parse_args()
+    if a._cpu_worker:
+        return cpu_worker(*json.loads(a._cpu_worker))
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_tot, rho, l_s, l_n, reps, what = WORKLOADS[a.workload]
+    if a.particles:
+        n_tot = a.particles
+    K, W = max(1, a.steps), max(3, a.warmup)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        c = run_cpu(rho, l_s, l_n, W, K)
+        line = {"impl": "reference", "metric": "particle-steps/sec (fp64)", "value": c["value"], "unit": "particle-steps/s",
+                "n_gpus": a.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * c["secs"] / K, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": a.workload, "what": what, "particles": n_tot, "phi": rho, "lambda_s": l_s, "lambda_n": l_n},
+                "cpu_baseline": {"value": c["value"], "unit": c["unit"], "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]},
+                "e2e": {"value": c["value"], "unit": c["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from active_particle_jamming_b200 import DeviceEngine
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == a.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- this rank's share. n_gpus > 1: the box is cut into n_gpus parts of n_tot / n_gpus particles.
+    n_loc = n_tot // world
+    parallelism = "single" if world == 1 else "replicas%d" % world
+    R, L, x, y, phi = synthetic_state(n_loc, rho, 12345 + rank)
+    Ls = [L] * reps
+    if reps > 1:
+        parts = [synthetic_state(n_loc, rho, 12345 + rank * reps + s) for s in range(reps)]
+        Ls = [p[1] for p in parts]
+        R, x, y, phi = (np.concatenate([p[k] for p in parts]) for k in (0, 2, 3, 4))
+
+    def pinned(arr):
+        t = torch.empty(arr.shape, dtype=torch.float64, pin_memory=True)
+        t.numpy()[...] = arr
+        return t.numpy()
+    host = {k: pinned(v) for k, v in dict(x=x, y=y, R=R, phi=phi).items()}
+
+    e = DeviceEngine(n_loc, Ls, n_systems=reps, device=local, seed=12345 + rank, max_neighbors=64)
+    e.upload(**host)
+    e.skip_self_term_once()
+    trelax, ttherm = (50, 50) if a.no_relax else RELAX                     # relax(): jamming.cpp:482-525
+    e.set_activity(0.0, l_n); e.step(trelax)
+    e.set_activity(l_s, l_n); e.set_ramp(ttherm); e.step(ttherm); e.set_ramp(0)
+    e.mark_origin(); e.set_reset_counter(0)
+
+    # ---- device-resident throughput
+    e.step(W)
+    c0 = e.counters()
+    smi = ClockSampler(local)
+    barrier()
+    t0w = time.time()
+    e.timer_begin()
+    e.step(K)
+    ms = e.timer_end()
+    barrier()
+    t1w = time.time()
+    c1 = e.counters()
+    ms = max_over_ranks(ms)
+    clocks = smi.window(t0w, t1w)
+    particles = sum_over_ranks(float(n_loc * reps))
+    value = particles * K / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (fused step kernel): event pair around every launch
+    n_full, list_max = e.list_stats(0)
+    kms, committed = e.time_step_kernel(min(max(K, 16), 512))
+    b_alg = 128.0 + 4.0 * n_full                                           # bytes per particle-step
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = n_loc * reps * b_alg / (kms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "apj_step_kernel", "kernel_ms": kms, "bytes_per_particle_step": b_alg, "n_full": n_full,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
+    try:
+        roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(a.workload)
+    except Exception:
+        pass
+
+    # ---- end to end: a whole job through the host-facing API, host buffers in, host buffers out
+    st_host = e.download()
+    up = {k: pinned(st_host[k]) for k in ("x", "y", "x_real", "y_real", "x0", "y0", "x_old", "y_old", "R", "phi", "cosp", "sinp", "vx", "vy")}
+    box_host = st_host["box"]
+    com = [e.get_com(s) for s in range(reps)]
+    barrier()
+    tj0 = time.perf_counter()
+    e.upload(box=box_host, **up)                                           # H2D: 14 fp64 + 1 int32 per particle
+    for s in range(reps):
+        e.set_com(s, com=com[s]["COM"], com0=com[s]["COM0"], com_old=com[s]["COM_old"])
+    done = 0
+    while done < K:                                                        # driver cadence: order/orientation/COM/MSD every 100 steps (:218-239)
+        n = min(100, K - done)
+        e.step(n); done += n
+        e.order_orientation(); e.msd(); e.get_com(0)
+    out = e.download()                                                     # D2H: full state
+    barrier()
+    tj1 = time.perf_counter()
+    tj = max_over_ranks(tj1 - tj0)
+    nb = n_loc * reps
+    e2e = {"value": particles * K / tj, "unit": "particle-steps/s", "h2d_bytes_per_step": (14 * 8 + 4) * nb / K,
+           "d2h_bytes_per_step": ((14 * 8 + 4) * nb + 40 * ((K + 99) // 100) * reps) / K, "job_seconds": tj,
+           "what": "apj_upload_state (pinned host SoA) + K x apj_step with order/orientation/MSD/COM read back every 100 steps + apj_download_state"}
+    assert np.all(np.isfinite(out["x"]))
+
+    line = {"metric": "particle-steps/sec (fp64)", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": a.workload, "what": what, "particles": int(particles), "particles_per_gpu": n_loc * reps, "phi": rho,
+                       "lambda_s": l_s, "lambda_n": l_n, "dt": 0.1, "parallelism": parallelism, "relax": [trelax, ttherm],
+                       "l2": "state + lists per GPU = %.0f MB, larger than the 126 MB L2: no flush between steps" % (n_loc * reps * (108 + 4 * n_full) / 1e6)
+                       if n_loc * reps * 150 > 200e6 else "state fits L2 (%.0f MB): L2-resident by nature of the workload, no flush" % (n_loc * reps * 150 / 1e6),
+                       "rebuilds_in_timed_region": c1["rebuilds"] - c0["rebuilds"], "list_max": list_max, "tuning": e.tuning()},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": c1["launches"] - c0["launches"], "clocks": clocks}
+    smi.stop()
+    if rank == 0 and world == 1 and not a.no_cpu:
+        c = run_cpu(rho, l_s, l_n, 200, 1500)
+        line["cpu_baseline"] = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample", "per_core")}
+    e.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

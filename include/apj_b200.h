@@ -2,7 +2,7 @@
  *
  * The reference (danielmccusker/active-particle-jamming) has no FFI layer: its hot path is a set
  * of `Engine` methods in one translation unit (code/jam/jamming.cpp) over header-only structs
- * (code/classes/*.h). This header is the boundary a host `Engine` binds instead of those
+ * (the headers of code/classes). This header is the boundary a host `Engine` binds instead of those
  * methods; every entry point names the reference code it replaces (file:line relative to the
  * reference root). INTEGRATION.md shows the reference-side binding.
  *
@@ -118,6 +118,11 @@ int apj_set_reset_counter(apj_engine* e, int32_t system, int64_t value); /* rela
 int apj_get_tuning(apj_engine* e, int32_t* out8);
 /* out[5] = {L, Lover2, lp, b, nbox}  (jamming.cpp:99-103) */
 int apj_get_geometry(apj_engine* e, int32_t system, double* out5);
+
+/* out[2] = {sum over particles of the full Verlet-list length (entries within rs; twice the number
+ *           of pairs of Cell::VerletList), longest list}: n_full = out[0] / N is the figure the
+ *           algorithmic-bytes roofline uses. */
+int apj_list_stats(apj_engine* e, int32_t system, int64_t* out2);
 
 /* Neighbour pair set of one system as a half list by particle id (the parity object of
  * SURVEY Q1): offsets[N+1], idx[cap] (partners j > i, ascending). *total receives the pair

@@ -1,0 +1,107 @@
+"""CUDA path (through the C ABI) against the committed golden vectors written by the REFERENCE's
+own code (tests/golden/make_golden.py). Gates of BASELINE.json north_star:
+  * neighbour-pair sets and cell lists: bit-exact;
+  * one step from identical state with identical injected noise: <= 1e-12 relative;
+  * observables: <= 1e-12 relative (sums in a different, fixed order), integer histograms exact."""
+import numpy as np
+import pytest
+
+from _util import (DEV2ORC, GOLDEN_CASES, device_from_state, golden_state, half_pairs, load_golden, rel_err,
+                   wrapped_abs_diff)
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12          # north_star: single step within 1e-12 relative
+V_FLOOR = 1e-2       # velocities are O(lambda_s) <= 1: relative to max(|v|, 1e-2)
+
+
+@pytest.fixture(scope="module", params=GOLDEN_CASES)
+def gold(request):
+    return load_golden(request.param)
+
+
+def check_state(d, ref, L, tol, what):
+    assert np.max(wrapped_abs_diff(d["x"], ref["x"], L)) <= tol * L, what + ": x"
+    assert np.max(wrapped_abs_diff(d["y"], ref["y"], L)) <= tol * L, what + ": y"
+    for f in ("x_real", "y_real", "x_old", "y_old", "x0", "y0"):
+        assert rel_err(d[f], ref[DEV2ORC[f]], floor=L) <= tol, what + ": " + f
+    for f in ("cosp", "sinp", "R"):
+        assert rel_err(d[f], ref[DEV2ORC[f]], floor=1.0) <= tol, what + ": " + f
+    dphi = np.abs(d["phi"] - ref["phi"])
+    assert np.max(np.minimum(dphi, np.abs(6.28318531 - dphi))) <= tol * 3.14159265, what + ": phi"
+    for f in ("vx", "vy"):
+        assert rel_err(d[f], ref[f], floor=V_FLOOR) <= tol, what + ": " + f
+
+
+def test_pair_set_and_cells_bit_exact(gold):
+    s0 = golden_state(gold, "s0_")
+    with device_from_state(s0) as e:
+        g = e.geometry()
+        assert (g["b"], g["nbox"]) == (int(s0["b"]), int(s0["nbox"])) and g["lp"] == s0["lp"] and g["L"] == s0["L"]
+        assert np.array_equal(e.pair_set(), half_pairs(gold["s0_vl_off"], gold["s0_vl_idx"]))
+        off, idx = e.cell_lists()
+        assert np.array_equal(off, gold["s0_cl_off"]) and np.array_equal(idx, gold["s0_cl_idx"])
+        assert np.array_equal(e.download(["box"])["box"], s0["box"])
+
+
+def test_single_step_within_1e12(gold):
+    s0 = golden_state(gold, "s0_")
+    with device_from_state(s0) as e:
+        e.step_injected(gold["noise"][0])
+        d = e.download()
+        check_state(d, golden_state(gold, "s1_"), s0["L"], TOL, "step 1")
+        c = e.get_com()
+        s1 = golden_state(gold, "s1_")
+        assert abs(c["COM"][0] - s1["COMx"]) <= TOL * s0["L"] and abs(c["COM"][1] - s1["COMy"]) <= TOL * s0["L"]
+
+
+def test_free_running_injected_steps(gold):
+    """K steps without resynchronisation: rebuilds must fall on the same steps as the reference's
+    (resetCounter sequence) and the trajectories stay together (round-off grows slowly)."""
+    s0 = golden_state(gold, "s0_")
+    cks = set(int(c) for c in gold["checkpoints"])
+    with device_from_state(s0) as e:
+        for k in range(gold["K"]):
+            e.step_injected(gold["noise"][k])
+            assert e.counters()["resetCounter"] == int(gold["resets"][k]), "rebuild step differs at %d" % k
+            if k + 1 in cks:
+                check_state(e.download(), golden_state(gold, "s%d_" % (k + 1)), s0["L"], 1e-9, "step %d" % (k + 1))
+        # the lists the device holds now were built at the same step, from the same positions
+        assert np.array_equal(e.pair_set(), half_pairs(gold["end_vl_off"], gold["end_vl_idx"]))
+
+
+def test_observables_on_reference_end_state(gold):
+    sK = golden_state(gold, "s%d_" % gold["K"])
+    N, L = gold["N"], sK["L"]
+    with device_from_state(sK) as e:
+        order, orient = e.order_orientation()
+        assert abs(order[0] - float(gold["order"])) <= TOL
+        assert np.max(np.abs(orient[0] - gold["orientation"])) <= TOL
+        assert rel_err(e.msd()[0], float(gold["msd"]), floor=1e-3) <= TOL
+        # Fluctuations::measureFluctuations: the recorded sequence gives V for each radius visited
+        seq, dens = gold["fluct_seq"], gold["rho"]
+        r, prev, k = 3.0, 0.0, 0
+        for row in seq:
+            if row[2] == 0 and k > 0:          # flush call: radius advanced, no sample (Q13)
+                r, prev, k = row[0], 0.0, 0
+                continue
+            expected = dens * 3.14159265 * r * r
+            V = e.fluct_area(r)[0]
+            want_sq = row[1] - prev            # (V - expectedV)^2 added by this call
+            assert abs((V - expected) ** 2 - want_sq) <= 1e-9 * max(1.0, want_sq)
+            prev, k = row[1], k + 1
+        # Correlations (cutoff 20 of the local build, jamming.cpp:153)
+        c = e.spatial_correlations(20.0)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            vel = c["vel_sum"][0] / c["counts"][0]
+            ori = c["ori_sum"][0] / c["counts"][0]
+        norm = 2 * L * L / (2 * 3.14159265 * 0.1 * float(N * N))
+        assert np.array_equal(np.isnan(vel), np.isnan(gold["corr_vel"]))      # empty bins are 0/0 in both (Q14)
+        ok = ~np.isnan(vel)
+        assert rel_err(vel[ok], gold["corr_vel"][ok], floor=1e-2) <= 1e-11
+        assert rel_err(ori[ok], gold["corr_ori"][ok], floor=1e-2) <= 1e-11
+        assert rel_err(c["pair_sum"][0] * norm, gold["corr_pair"], floor=1e-3) <= 1e-11
+        # integer histograms: exact
+        vh = e.vel_hist(gold["l_s"] / 50.0)[0]
+        assert np.array_equal(vh, np.rint(gold["vel_dist"] * N).astype(np.int64))
+        assert np.array_equal(e.occupancy_hist()[0], gold["dens_dist"].astype(np.int64))

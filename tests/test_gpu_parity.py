@@ -1,0 +1,277 @@
+"""CUDA path vs the oracle (oracle/apj_oracle.c, itself pinned bit-for-bit to the reference) on
+seeded synthetic systems, every call through the C ABI. Small sizes compare full state; the sizes
+BASELINE.json names (65 536 at phi = 1.0, 1 048 576 at phi = 0.9) are compared directly too -- the
+O(N) oracle finishes them in seconds -- plus size-independent properties (Newton's third law,
+COM consistency, determinism, in-box positions)."""
+import numpy as np
+import pytest
+
+from _util import DEV2ORC, device_from_state, random_system, rel_err, wrapped_abs_diff
+from oracle.pyoracle import PI, OracleSim
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def relaxed_oracle(N, rho, seed, l_s=0.05, l_n=0.5, presteps=60):
+    """Random synthetic configuration pushed through `presteps` oracle steps (the first
+    ones at CFself = 0, like relax()) so overlaps are physical and xnew = cosp holds."""
+    R, L, x, y, phi = random_system(N, rho, seed)
+    o = OracleSim.from_arrays(R, x, y, phi, rho)
+    o.topology()
+    o.assign()
+    o.build()
+    o.mark_origin()
+    rng = np.random.default_rng(seed + 1)
+    o.set_params(0.0, l_n)
+    for _ in range(presteps // 2):
+        o.step(rng.uniform(-PI, PI, N))
+    o.set_params(l_s, l_n)
+    for _ in range(presteps - presteps // 2):
+        o.step(rng.uniform(-PI, PI, N))
+    o.mark_origin()
+    return o, rng
+
+
+def assert_state_close(d, o, L, tol, what=""):
+    assert np.max(wrapped_abs_diff(d["x"], o.x, L)) <= tol * L, what + " x"
+    assert np.max(wrapped_abs_diff(d["y"], o.y, L)) <= tol * L, what + " y"
+    for f in ("x_real", "y_real", "x_old", "y_old", "x0", "y0"):
+        assert rel_err(d[f], getattr(o, DEV2ORC[f]), floor=L) <= tol, what + " " + f
+    assert rel_err(d["cosp"], o.cosp) <= tol and rel_err(d["sinp"], o.sinp) <= tol, what + " cos/sin"
+    dphi = np.abs(d["phi"] - o.phi)
+    assert np.max(np.minimum(dphi, np.abs(6.28318531 - dphi))) <= tol * PI, what + " phi"
+    assert rel_err(d["vx"], o.vx, floor=1e-2) <= tol and rel_err(d["vy"], o.vy, floor=1e-2) <= tol, what + " v"
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8])
+@pytest.mark.parametrize("N,rho", [(4096, 0.9), (1500, 1.0)])
+def test_step_by_step_resynchronised(N, rho, lanes):
+    """Every step starts from the oracle's state: pair sets bit-exact after each rebuild, each single
+    step within 1e-12 (gate 2 of north_star), for every lanes-per-particle variant of the kernel."""
+    o, rng = relaxed_oracle(N, rho, seed=N + lanes, l_s=0.5, l_n=0.3)
+    L = o.scalars()["L"]
+    e = device_from_state(o.state(), lanes_per_particle=lanes)
+    try:
+        o.assign(); o.build()
+        assert np.array_equal(e.pair_set(), o.pair_set())
+        for k in range(12):
+            e.close()
+            e = device_from_state(o.state(), lanes_per_particle=lanes)
+            nz = rng.uniform(-PI, PI, N)
+            rebuilt = o.step(nz)
+            e.step_injected(nz)
+            assert_state_close(e.download(), o, L, TOL, "step %d" % k)
+            assert e.counters()["resetCounter"] == o.scalars()["resetCounter"]
+            if rebuilt:
+                assert np.array_equal(e.pair_set(), o.pair_set())
+                assert np.array_equal(e.download(["box"])["box"], o.box)
+            sc, c = o.scalars(), e.get_com()
+            assert abs(c["COM"][0] - sc["COMx"]) <= TOL * L and abs(c["COM"][1] - sc["COMy"]) <= TOL * L
+    finally:
+        e.close()
+        o.close()
+
+
+@pytest.mark.parametrize("flags", [0, 1])   # CUDA graph / direct launches
+def test_free_running_philox_matches_oracle(flags):
+    """apj_step (Philox4x32-10 noise generated in the kernel, speculative multi-step launches with the
+    on-device rebuild) against the oracle drawing the same counter-based stream on the CPU."""
+    N, rho, seed = 4096, 0.9, 99
+    o, _ = relaxed_oracle(N, rho, seed=3, l_s=0.3, l_n=0.5)
+    L = o.scalars()["L"]
+    with device_from_state(o.state(), seed=seed, flags=flags) as e:
+        first = e.counters()["step"]
+        assert first == 0
+        o.run_philox(seed, 0, 1)
+        e.step(1)
+        assert_state_close(e.download(), o, L, TOL, "philox step 1")        # same noise bits -> 1e-12
+        nreb = o.run_philox(seed, 1, 399)
+        e.step(399)
+        c = e.counters()
+        assert c["step"] == 400
+        assert c["resetCounter"] == o.scalars()["resetCounter"] and nreb > 0  # rebuilds on the same steps
+        assert_state_close(e.download(), o, L, 1e-7, "philox step 400")     # round-off grows along the run
+        assert np.array_equal(e.pair_set(), o.pair_set())
+    o.close()
+
+
+def test_replicas_equal_single_systems():
+    """n_systems > 1 (phase-diagram sweep batching): every replica evolves exactly like the same
+    system alone -- bit-identical, the block decomposition and reduction order are per system."""
+    N = 2048
+    specs = [(0.84, 0.1, 0.2, 5), (0.9, 0.5, 0.5, 6), (1.0, 1.0, 0.05, 7)]
+    os_ = [relaxed_oracle(N, rho, seed=sd, l_s=ls, l_n=ln)[0] for rho, ls, ln, sd in specs]
+    from active_particle_jamming_b200 import DeviceEngine
+    Ls = [o.scalars()["L"] for o in os_]
+    rng = np.random.default_rng(0)
+    noise = rng.uniform(-PI, PI, (20, len(specs), N))
+    batch = DeviceEngine(N, Ls, n_systems=len(specs))
+    batch.set_activity([s[1] for s in specs], [s[2] for s in specs])
+    st = [o.state() for o in os_]
+    batch.upload(box=np.concatenate([s["box"] for s in st]), **{d: np.concatenate([s[k] for s in st]) for d, k in DEV2ORC.items()})
+    for i, s in enumerate(st):
+        batch.set_com(i, com=[s["COMx"], s["COMy"]], com0=[s["COM0x"], s["COM0y"]], com_old=[s["COMoldx"], s["COMoldy"]])
+    for k in range(20):
+        batch.step_injected(noise[k].ravel())
+    db = batch.download()
+    for i, s in enumerate(st):
+        with device_from_state(s) as single:
+            for k in range(20):
+                single.step_injected(noise[k, i])
+            ds = single.download()
+            for f in ds:
+                assert np.array_equal(ds[f], db[f][i * N:(i + 1) * N]), (i, f)
+            assert single.counters()["resetCounter"] == batch.counters(i)["resetCounter"]
+            assert np.array_equal(single.pair_set(), batch.pair_set(i))
+    o_ord, o_vec = batch.order_orientation()
+    for i, o in enumerate(os_):
+        for k in range(20):
+            o.step(noise[k, i])
+        assert abs(o_ord[i] - o.order()) <= 1e-9 and np.max(np.abs(o_vec[i] - o.orientation())) <= 1e-9
+        o.close()
+    batch.close()
+
+
+def test_relax_schedule_ramp_and_first_step():
+    """relax() (jamming.cpp:482-525): CFself = 0 phase, then the linear ramp (:518); and the very first
+    step of a fresh Engine, whose alignment sum has no self term (Cell.h:75)."""
+    N, rho = 1024, 0.9
+    R, L, x, y, phi = random_system(N, rho, 21)
+    o = OracleSim.from_arrays(R, x, y, phi, rho)
+    o.topology(); o.assign(); o.build()
+    from active_particle_jamming_b200 import DeviceEngine
+    e = DeviceEngine(N, L, seed=5)
+    # relax() starts with x_old = x_real = -100 (Cell.h:64-67): the first skin test always fires (Q7)
+    e.upload(x=o.x, y=o.y, R=o.R, phi=o.phi, cosp=o.cosp, sinp=o.sinp, box=o.box, x_old=o.xo, y_old=o.yo,
+             x_real=o.xr, y_real=o.yr, x0=o.x0, y0=o.y0)
+    o.set_com([0, 0], [0, 0], [0, 0]); e.set_com(0, com=[0, 0], com0=[0, 0], com_old=[0, 0])
+    e.skip_self_term_once()
+    CF, trelax, ttherm = 0.4, 30, 40
+    o.set_params(0.0, 0.5); e.set_activity(0.0, 0.5)
+    o.run_philox(5, 0, trelax); e.step(trelax)
+    assert_state_close(e.download(), o, L, 1e-9, "CFself=0 phase")
+    e.set_activity(CF, 0.5); e.set_ramp(ttherm)
+    for t_ in range(ttherm):
+        o.set_params(CF - (ttherm - t_) * CF / ttherm, 0.5)                 # jamming.cpp:518
+        o.run_philox(5, trelax + t_, 1)
+    e.step(ttherm)
+    assert_state_close(e.download(), o, L, 1e-8, "ramp phase")
+    o.set_params(CF, 0.5)
+    o.run_philox(5, trelax + ttherm, 5); e.step(5)
+    assert_state_close(e.download(), o, L, 1e-8, "after ramp")
+    assert e.counters()["resetCounter"] == o.scalars()["resetCounter"]
+    e.close(); o.close()
+
+
+def test_mark_origin_and_observables_vs_oracle():
+    N, rho = 4096, 0.9
+    o, rng = relaxed_oracle(N, rho, seed=17, l_s=0.4, l_n=0.2)
+    with device_from_state(o.state()) as e:
+        e.mark_origin(); o.mark_origin()                                    # start() :191-203
+        c, sc = e.get_com(), o.scalars()
+        L = sc["L"]
+        assert abs(c["COM0"][0] - sc["COM0x"]) <= TOL * L and abs(c["COM_old"][1] - sc["COMoldy"]) <= TOL * L
+        for k in range(40):
+            nz = rng.uniform(-PI, PI, N)
+            o.step(nz); e.step_injected(nz)
+        order, orient = e.order_orientation()
+        assert abs(order[0] - o.order()) <= 1e-9 and np.max(np.abs(orient[0] - o.orientation())) <= 1e-9
+        assert rel_err(e.msd()[0], o.msd(), floor=1e-3) <= 1e-8
+        # observables from IDENTICAL state: re-upload the oracle's state, then 1e-12
+        with device_from_state(o.state()) as e2:
+            order, orient = e2.order_orientation()
+            assert abs(order[0] - o.order()) <= TOL and np.max(np.abs(orient[0] - o.orientation())) <= TOL
+            assert rel_err(e2.msd()[0], o.msd(), floor=1e-3) <= TOL
+            for radius in (3.0, 7.5, L / 4, L / 2):
+                assert rel_err(e2.fluct_area(radius)[0], o.fluct_area(radius), floor=1.0) <= 1e-11
+            o.assign()
+            assert np.array_equal(e2.occupancy_hist()[0], o.density_distribution().astype(np.int64))
+            assert np.array_equal(e2.vel_hist(0.4 / 50)[0], np.rint(o.vel_dist(0.4) * N).astype(np.int64))
+            off_o, idx_o = o.cell_lists(); off_d, idx_d = e2.cell_lists()
+            assert np.array_equal(off_o, off_d) and np.array_equal(idx_o, idx_d)
+
+
+def test_error_paths():
+    from active_particle_jamming_b200 import ApjError, DeviceEngine
+    with pytest.raises(ApjError) as ei:
+        DeviceEngine(64, 10.0)                                              # b = floor(10/5.6) = 1 < 3 (jamming.cpp:359)
+    assert ei.value.code == -1
+    with pytest.raises(ApjError) as ei:
+        DeviceEngine(1024, 60.0, lanes_per_particle=3)
+    assert ei.value.code == -1
+    e = DeviceEngine(1024, 60.0)
+    with pytest.raises(ApjError) as ei:
+        e.step(1)                                                           # no state uploaded
+    assert ei.value.code == -4
+    with pytest.raises(ApjError):
+        e.upload(x=np.zeros(1024), y=np.zeros(1024))                        # R, phi missing
+    e.close()
+    # list capacity: all particles in one spot -> more neighbours than max_neighbors
+    R, L, x, y, phi = random_system(1024, 0.9, 3)
+    e = DeviceEngine(1024, L, max_neighbors=8)
+    with pytest.raises(ApjError) as ei:
+        e.upload(x=x, y=y, R=R, phi=phi)
+    assert ei.value.code == -3 and "max_neighbors" in str(ei.value)
+    e.close()
+    with device_from_state(relaxed_oracle(1024, 0.9, 1)[0].state()) as e:
+        with pytest.raises(ApjError) as ei:
+            e.spatial_correlations(19.0)
+        assert ei.value.code == -1
+
+
+def test_inhomogeneous_density_grows_the_tile():
+    """A clustered configuration (empty half box) forces tiles far from the mean occupancy: the
+    shared-memory tile capacity must adapt, and the pair set must still be exact."""
+    N, rho = 4096, 0.45
+    R, L, x, y, phi = random_system(N, rho, 31)
+    x = x / 2 - L / 4                                                       # everything in the left half
+    o = OracleSim.from_arrays(R, x, y, phi, rho)
+    o.topology(); o.assign(); o.build()
+    from active_particle_jamming_b200 import DeviceEngine
+    with DeviceEngine(N, L, max_neighbors=96) as e:
+        e.set_activity(0.1, 0.1)
+        e.upload(x=o.x, y=o.y, R=o.R, phi=o.phi, cosp=o.cosp, sinp=o.sinp)
+        assert np.array_equal(e.pair_set(), o.pair_set())
+        t = e.tuning()
+        assert t["tile_max"] <= t["tile_cap"]
+    o.close()
+
+
+@pytest.mark.parametrize("N,rho", [(65536, 1.0), (1048576, 0.9)])
+def test_full_size_parity_and_properties(N, rho):
+    """BASELINE.json configs[1] and [2] sizes: direct comparison with the oracle (pair set bit-exact,
+    single step 1e-12) and size-independent properties of a free run."""
+    l_s, l_n = 0.05, 0.5
+    o, rng = relaxed_oracle(N, rho, seed=N % 1000, l_s=l_s, l_n=l_n, presteps=12)
+    sc = o.scalars(); L = sc["L"]
+    o.assign(); o.build()
+    with device_from_state(o.state(), seed=77) as e:
+        assert np.array_equal(e.pair_set(), o.pair_set())                   # gate 1 at full size
+        nz = rng.uniform(-PI, PI, N)
+        o.step(nz); e.step_injected(nz)
+        assert_state_close(e.download(), o, L, TOL, "full-size step")       # gate 2 at full size
+    # free run with on-device Philox noise and rebuilds; twice, for determinism
+    runs = []
+    for rep in range(2):
+        with device_from_state(o.state(), seed=77) as e:
+            e.step(150)
+            runs.append((e.download(), e.counters(), e.get_com()))
+    (d, cnt, c), (d2, cnt2, _) = runs
+    for f in d:
+        assert np.array_equal(d[f], d2[f]), "run-to-run difference in " + f
+    assert cnt2["resetCounter"] == cnt["resetCounter"]
+    assert np.all(d["x"] >= -L / 2) and np.all(d["x"] < L / 2) and np.all(d["y"] >= -L / 2) and np.all(d["y"] < L / 2)
+    # x - x_real is a whole number of box lengths (PBC is a single wrap per step, Cell.h:168-175)
+    kx = (d["x_real"] - d["x"]) / L
+    assert np.max(np.abs(kx - np.rint(kx))) < 1e-9
+    # COM held by the engine == mean of x_real (calculate_COM, jamming.cpp:761-774)
+    assert abs(c["COM"][0] - d["x_real"].mean()) <= 1e-11 * L and abs(c["COM"][1] - d["y_real"].mean()) <= 1e-11 * L
+    # Newton's third law: sum_i (R_i v_i - CFself R_i n_i) = sum of pair forces = 0
+    fx = np.sum(d["R"] * d["vx"] - l_s * d["R"] * d["cosp"]); fy = np.sum(d["R"] * d["vy"] - l_s * d["R"] * d["sinp"])
+    scale = np.sum(np.abs(d["R"] * d["vx"])) + 1.0
+    assert abs(fx) <= 1e-11 * scale and abs(fy) <= 1e-11 * scale
+    assert np.allclose(d["cosp"] ** 2 + d["sinp"] ** 2, 1.0, atol=1e-14)
+    assert np.allclose(np.cos(d["phi"]), d["cosp"], atol=1e-14)
+    assert cnt["rebuilds"] >= 1 and cnt["overflow"] == 0 and cnt["step"] == 150
+    o.close()
