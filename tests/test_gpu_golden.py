@@ -56,8 +56,11 @@ def test_single_step_within_1e12(gold):
 
 
 def test_free_running_injected_steps(gold):
-    """K steps without resynchronisation: rebuilds must fall on the same steps as the reference's
-    (resetCounter sequence) and the trajectories stay together (round-off grows slowly)."""
+    """K <= 100 steps without resynchronisation: rebuilds must fall on the same steps as the
+    reference's (resetCounter sequence) and the trajectories stay together. The orientation dynamics
+    is chaotic: 1-ulp differences in cos/sin (CUDA libm vs glibc) grow ~1 decade per 25 steps at
+    lambda_n = 0.5 and faster at lambda_n = 1 (measured by perturbing the oracle itself, DESIGN.md
+    "Parity"), so the free-running bound is 1e-6; the 1e-12 gate is the single-step test above."""
     s0 = golden_state(gold, "s0_")
     cks = set(int(c) for c in gold["checkpoints"])
     with device_from_state(s0) as e:
@@ -65,7 +68,7 @@ def test_free_running_injected_steps(gold):
             e.step_injected(gold["noise"][k])
             assert e.counters()["resetCounter"] == int(gold["resets"][k]), "rebuild step differs at %d" % k
             if k + 1 in cks:
-                check_state(e.download(), golden_state(gold, "s%d_" % (k + 1)), s0["L"], 1e-9, "step %d" % (k + 1))
+                check_state(e.download(), golden_state(gold, "s%d_" % (k + 1)), s0["L"], 1e-6, "step %d" % (k + 1))
         # the lists the device holds now were built at the same step, from the same positions
         assert np.array_equal(e.pair_set(), half_pairs(gold["end_vl_off"], gold["end_vl_idx"]))
 
