@@ -11,9 +11,12 @@
 //           column plus the <= 6 contiguous particle runs ("pieces") that hold every cell
 //           adjacent to the block's cells. The step kernel copies the pieces into shared
 //           memory with TMA bulk copies; all neighbour gathers then hit shared memory.
-//   list    full Verlet list in TILE-LOCAL 16-bit slots, two entries per 32-bit word, sorted by
-//           distance at build time; word w of particle p sits at [w / G][p * G + w % G] of the
-//           block's [round][tb threads] array, so each sweep round is one conflict-free row
+//   list    full Verlet list as TILE-LOCAL 16-bit entries (byte offset of the neighbour's 16-byte
+//           tile slot; slot 0 = sentinel, used to pad odd lists), two per 32-bit word, sorted by
+//           distance at build time. Word w of particle p belongs to lane sub = w % G of the G
+//           lanes sweeping p, as that lane's word k = w / G; a thread's words are stored as uint4
+//           quads in the block's [quad][tb threads] array: one coalesced 16-byte load per thread
+//           fetches 8 entries, issued before the tile has landed
 // One SysCtl per batched system (replica) holds geometry, parities, COM and the step counter;
 // kernels read it at entry, the last block of the step kernel commits to it.
 #pragma once
@@ -30,7 +33,7 @@
 struct __align__(64) TileDesc {
     int g0;         // first particle (absolute index) of the block
     int n;          // particles in the block (1..ppb)
-    int own_slot;   // tile slot of particle g0
+    int own_slot;   // tile slot (1-based) of particle g0
     int info;       // npieces | wraps << 8 | list words of the longest list << 16
     int pstart[APJ_MAX_PIECES];  // absolute particle index where each piece starts
     int plen[APJ_MAX_PIECES];    // particles in each piece (tile slots are the concatenation)
@@ -66,11 +69,11 @@ struct DevState {
     int G;                 // lanes per particle in the sweep (1, 2, 4 or 8)
     int tb;                // threads per work block of the step kernel (128 or 256)
     int ppb;               // particles per work block = tb / G
-    int smem_rounds;       // list rows staged in shared memory (the rest, rare, is read from global)
     int maxblk;            // work blocks reserved per system (N/ppb + b + 1)
     int S;                 // list capacity per particle (even)
-    int max_rounds;        // ceil(S/2 / G): rows of the per-block list array
-    int tile_cap;          // shared-memory tile capacity in slots
+    int max_rounds;        // ceil(S/2 / G): list words one lane can hold
+    int max_quads;         // ceil(max_rounds / 4): uint4 rows of the per-block list array
+    int tile_cap;          // shared-memory tile capacity in slots (<= 4094; slot 0 is the sentinel)
     double dt, rn2, rs2, skin;  // skin = rs - rn (jamming.cpp:611)
     unsigned long long seed;
     SysCtl* ctl;
@@ -85,7 +88,7 @@ struct DevState {
     int* ID[2];
     int* BOX[2];  // internal cell index cy + cx*b (columns contiguous)
     TileDesc* tiles;      // n_sys * maxblk
-    unsigned* list32;     // n_sys * maxblk * max_rounds * tb
+    unsigned* list32;     // n_sys * maxblk * max_quads * tb uint4
     int* cnt;             // per particle
     int* boxnew;
     int* perm;
@@ -93,6 +96,7 @@ struct DevState {
     int* cell_start;   // per system nbox+1 entries, absolute particle indices
     int* cell_cursor;
     int* col_blk;      // per system b+1 entries: first work block of each column
+    int* chunk_sums;   // per system scan_chunks entries: scratch of the cell scan
     double4* partials;  // per work block {sum x_real, sum y_real, top1 d2, top2 d2}
     double4* gpartials; // per group of 32 work blocks
     unsigned* gticket;  // per group arrival counter (zero between launches)
@@ -144,9 +148,9 @@ __device__ __forceinline__ void apj_top2_merge(double& a1, double& a2, double b1
     else { a2 = fmax(a2, b1); }
 }
 
-// tile slot of absolute particle index j (j must lie in one of the pieces)
+// tile slot (1-based; 0 is the sentinel) of absolute particle index j (j must lie in one of the pieces)
 __device__ __forceinline__ int apj_slot_of(const TileDesc& d, int j) {
-    int off = 0;
+    int off = 1;
     const int npieces = d.info & 0xff;
 #pragma unroll
     for (int p = 0; p < APJ_MAX_PIECES; p++) {
@@ -172,15 +176,17 @@ __device__ __forceinline__ void apj_bulk_g2s(void* dst_smem, const void* src_gme
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(apj_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(apj_smem_addr(bar)) : "memory");
 }
-__device__ __forceinline__ void apj_mbar_wait(unsigned long long* bar, unsigned parity) {
+// `dep` is threaded through the wait as an in/out operand: shared-memory loads whose address is
+// derived from it cannot be scheduled before the barrier completes.
+__device__ __forceinline__ void apj_mbar_wait(unsigned long long* bar, unsigned parity, unsigned& dep) {
     unsigned done = 0;
     while (!done) {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(apj_smem_addr(bar)), "r"(parity) : "memory");
+            "}\n" : "=r"(done), "+r"(dep) : "r"(apj_smem_addr(bar)), "r"(parity) : "memory");
     }
 }
 
@@ -189,4 +195,6 @@ struct ApjLaunch { cudaStream_t stream; long long* launch_counter; };
 void apj_launch_step(const DevState& st, const ApjLaunch& l, const double* noise_by_id, int always_full);
 void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nbox, int max_b);
 int apj_configure_kernels(const DevState& st);
+int apj_configure_rebuild(const DevState& st);
 int apj_max_list_capacity();
+int apj_scan_chunk_cells();

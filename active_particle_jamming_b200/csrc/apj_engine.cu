@@ -114,14 +114,31 @@ static int launch_group(apj_engine* e) {
 
 static int build_group_graph(apj_engine* e);
 
-// Shared-memory tile capacity follows the decomposition: the launch configuration (and the graph)
-// is rebuilt when a rebuild produced a tile larger than the capacity (nothing was committed, the
-// system is still stale) or when the capacity is far above what the current tiles need.
-static int set_tile_cap(apj_engine* e, int cap) {
-    cap = (cap + 7) / 8 * 8;
-    if (cap > 4096) return fail(e, APJ_E_OVERFLOW, "a work block needs more than 4096 shared-memory slots (density too inhomogeneous for the tile)");
-    e->st.tile_cap = cap;
-    if (apj_configure_kernels(e->st) != 0) return fail(e, APJ_E_CUDA, "cannot reserve shared memory for the tile");
+// Shared-memory tile capacity follows the decomposition. The capacity decides how many work
+// blocks fit one SM (227 KB of shared memory, 1 KB reserved per block), so it is set to the LARGEST
+// value that still reaches the block count the current tiles allow: full occupancy, maximum slack
+// before a denser tile forces a re-launch. The launch configuration (and the graph) is rebuilt
+// when a rebuild produced a tile larger than the capacity (nothing was committed, the system is
+// still stale) or when a smaller capacity would fit one more block per SM.
+static int blocks_per_sm(const DevState& st, int cap) {
+    const size_t per_block = (size_t)(cap + 1) * 48 + (st.G > 1 ? (size_t)st.ppb * 32 : 0) + 1024 + 512;
+    const int by_smem = (int)((size_t)233472 / per_block);
+    return std::max(1, std::min(by_smem, st.tb == 256 ? 4 : 8));     // register file: __launch_bounds__ of the step kernel
+}
+static int best_tile_cap(const DevState& st, int need) {
+    need = std::min(std::max(need + need / 32 + 8, 64), 4094);
+    const int target = blocks_per_sm(st, need);
+    int lo = need, hi = 4094;                                         // largest cap with the same block count
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) / 2;
+        if (blocks_per_sm(st, mid) >= target) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+static int set_tile_cap(apj_engine* e, int need) {
+    if (need > 4094) return fail(e, APJ_E_OVERFLOW, "a work block needs more than 4094 shared-memory slots (density too inhomogeneous for the tile)");
+    e->st.tile_cap = e->cfg.tile_slots > 0 ? std::max(e->cfg.tile_slots, need) : best_tile_cap(e->st, need);
+    if (apj_configure_kernels(e->st) != 0 || apj_configure_rebuild(e->st) != 0) return fail(e, APJ_E_CUDA, "cannot reserve shared memory for the tile");
     if (e->group_exec) { cudaGraphExecDestroy(e->group_exec); e->group_exec = nullptr; }
     return build_group_graph(e);
 }
@@ -131,7 +148,7 @@ static int repair_tile_overflow(apj_engine* e, int* repaired) {
     int need = 0;
     for (auto& c : e->hctl) if (c.overflow & 2) need = std::max(need, c.tile_max);
     if (!need) return APJ_OK;
-    if (int rc = set_tile_cap(e, need + need / 8 + 16)) return rc;
+    if (int rc = set_tile_cap(e, need)) return rc;
     for (auto& c : e->hctl) c.overflow &= ~2;
     *repaired = 1;
     return push_ctl(e);
@@ -140,8 +157,7 @@ static int maybe_shrink_tile_cap(apj_engine* e) {
     if (e->cfg.tile_slots > 0) return APJ_OK;
     int need = 0;
     for (auto& c : e->hctl) need = std::max(need, c.tile_max);
-    const int want = need + need / 10 + 16;
-    if (need > 0 && want < e->st.tile_cap * 0.85) return set_tile_cap(e, want);
+    if (need > 0 && blocks_per_sm(e->st, best_tile_cap(e->st, need)) > blocks_per_sm(e->st, e->st.tile_cap)) return set_tile_cap(e, need);
     return APJ_OK;
 }
 
@@ -183,7 +199,7 @@ extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** o
     st.tb = st.G == 1 ? 256 : 128;
     st.ppb = st.tb / st.G;
     st.max_rounds = (st.S / 2 + st.G - 1) / st.G;
-    st.smem_rounds = std::min(st.max_rounds, (12 + st.G - 1) / st.G + (st.G > 2 ? 1 : 0));   // 24+ entries per particle
+    st.max_quads = (st.max_rounds + 3) / 4;
     // Engine constants exactly as the reference derives them (jamming.cpp:57, :112-115, :611)
     const double dt = cfg->dt > 0 ? cfg->dt : 0.1;
     const double rn = cfg->rn > 0 ? cfg->rn : 2.8;
@@ -218,9 +234,8 @@ extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** o
         double ppc = 0;
         for (int s = 0; s < st.n_sys; s++) ppc = std::max(ppc, (double)st.N / e->hctl[s].nbox);
         const double mean = 3.0 * (st.ppb / ppc + 3.0) * ppc;   // three columns x (block rows + halo rows)
-        const int want = (int)(mean + 4.0 * std::sqrt(mean)) + 16;
-        st.tile_cap = cfg->tile_slots > 0 ? cfg->tile_slots : want;   // grows / shrinks with ctl.tile_max
-        st.tile_cap = std::min((st.tile_cap + 7) / 8 * 8, 4096);
+        const int want = std::min((int)(mean + 4.0 * std::sqrt(mean)) + 16, 4094);
+        st.tile_cap = cfg->tile_slots > 0 ? std::min(cfg->tile_slots, 4094) : best_tile_cap(st, want);   // follows ctl.tile_max later
     }
 
     int rc = APJ_OK;
@@ -235,8 +250,9 @@ extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** o
         A(dev_alloc(e, &st.BOX[h], (size_t)st.ntot));
     }
     A(dev_alloc(e, &st.tiles, (size_t)st.n_sys * st.maxblk));
-    A(dev_alloc(e, &st.list32, (size_t)st.n_sys * st.maxblk * st.max_rounds * st.tb));
+    A(dev_alloc(e, &st.list32, (size_t)st.n_sys * st.maxblk * st.max_quads * 4 * st.tb));
     A(dev_alloc(e, &st.col_blk, (size_t)cols));
+    A(dev_alloc(e, &st.chunk_sums, (size_t)st.n_sys * ((e->max_nbox + apj_scan_chunk_cells() - 1) / apj_scan_chunk_cells())));
     A(dev_alloc(e, &st.cnt, (size_t)st.ntot));
     A(dev_alloc(e, &st.boxnew, (size_t)st.ntot));
     A(dev_alloc(e, &st.perm, (size_t)st.ntot));
@@ -251,7 +267,7 @@ extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** o
     A(apj_obs_alloc(&e->obs, st, e->stream, e->allocs));
 #undef A
     if (rc != APJ_OK) return bail(rc);
-    if (apj_configure_kernels(st) != 0) { e->err = "apj_create: cannot reserve shared memory for the tile (tile_slots too large?)"; return bail(APJ_E_CUDA); }
+    if (apj_configure_kernels(st) != 0 || apj_configure_rebuild(st) != 0) { e->err = "apj_create: cannot reserve shared memory for the tile (tile_slots too large?)"; return bail(APJ_E_CUDA); }
     if (push_ctl(e) != APJ_OK) return bail(APJ_E_CUDA);
     if (build_group_graph(e) != APJ_OK) return bail(APJ_E_CUDA);
     *out = e;
@@ -532,7 +548,7 @@ extern "C" int apj_get_tuning(apj_engine* e, int32_t* o) {
     int tm = 0, nb = 0;
     for (auto& c : e->hctl) { tm = std::max(tm, c.tile_max); nb += c.nblk; }
     o[0] = e->st.G; o[1] = e->st.tb; o[2] = e->st.ppb; o[3] = e->st.tile_cap; o[4] = tm;
-    o[5] = (int)(e->st.tile_cap * 48 + (size_t)e->st.smem_rounds * e->st.tb * 4 + (size_t)e->st.ppb * 32); o[6] = nb; o[7] = e->m;
+    o[5] = (int)((e->st.tile_cap + 1) * 48 + (e->st.G > 1 ? (size_t)e->st.ppb * 32 : 0)); o[6] = nb; o[7] = e->m;
     return APJ_OK;
 }
 extern "C" int apj_set_reset_counter(apj_engine* e, int32_t s, int64_t v) {
@@ -587,7 +603,7 @@ extern "C" int apj_get_pair_list(apj_engine* e, int32_t s, int64_t* offsets, int
     const SysCtl& c = e->hctl[s];
     const long long o = (long long)s * st.N;
     const size_t N = st.N;
-    const size_t words_per_blk = (size_t)st.max_rounds * st.tb;
+    const size_t words_per_blk = (size_t)st.max_quads * 4 * st.tb;
     std::vector<int> id(N), cnt(N);
     std::vector<TileDesc> tiles(c.nblk);
     std::vector<unsigned> lst(words_per_blk * c.nblk);
@@ -605,9 +621,9 @@ extern "C" int apj_get_pair_list(apj_engine* e, int32_t s, int64_t* offsets, int
             const long long g = d.g0 + t - o;
             if (g < 0 || g >= (long long)N) return fail(e, APJ_E_STATE, "apj_get_pair_list: tile outside its system");
             for (int k = 0; k < cnt[g]; k++) {
-                const int wi = k >> 1;
-                const unsigned w = lst[blk * words_per_blk + (size_t)(wi / st.G) * st.tb + (size_t)t * st.G + (wi % st.G)];
-                int slot = (k & 1) ? (int)(w >> 16) : (int)(w & 0xffffu);
+                const int wi = k >> 1, sub = wi % st.G, kk = wi / st.G;
+                const unsigned w = lst[blk * words_per_blk + ((size_t)(kk >> 2) * st.tb + (size_t)t * st.G + sub) * 4 + (kk & 3)];
+                int slot = (int)(((k & 1) ? (w >> 16) : (w & 0xffffu)) >> 4) - 1;   // entries are (1-based slot) * 16
                 long long j = -1;
                 for (int p = 0; p < (d.info & 0xff); p++) {
                     if (slot < d.plen[p]) { j = (long long)d.pstart[p] + slot - o; break; }

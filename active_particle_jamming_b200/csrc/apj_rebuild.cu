@@ -3,14 +3,16 @@
 // counting sort that physically re-orders every particle array into cell order:
 //
 //   bin_count    exact nearest-box-centre binning + atomic histogram of cells
-//   cell_scan    exclusive prefix scan of the histogram -> cell_start / cell_cursor
+//   cell_scan    exclusive prefix scan of the histogram -> cell_start / cell_cursor (chunk sums,
+//                scan of the chunk sums, in-chunk scan: three launches, any number of cells)
 //   scatter      slot = atomicAdd(cursor[cell]) -> perm
 //   cell_sort    sort each cell's slots by particle id (== Box::CellList ascending order;
 //                makes the layout, and with it every reduction order, deterministic)
 //   reorder      gather all SoA arrays through perm into the other ping-pong half
 //   make_tiles   cut every cell column into work blocks of <= ppb particles and record, per
 //                block, the contiguous particle runs that cover all adjacent cells (TileDesc)
-//   verlet_build 3x3 cell sweep, d2 < rs2, full list sorted by distance, stored as tile slots
+//   verlet_build 3x3 cell sweep out of a shared-memory tile, d2 < rs2, full list stored as tile slots,
+//                first coordination shell first
 //   finish       flip parities, COM_old = COM, resetCounter++, clear `stale`
 //
 // Every kernel exits at once for systems whose ctl.stale is 0, so the chain can sit in the
@@ -22,6 +24,7 @@ namespace {
 constexpr int RB_BLOCK = 128;
 constexpr int SCAN_BLOCK = 1024;
 constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_CHUNK = SCAN_BLOCK * SCAN_ITEMS;   // cells scanned by one block
 constexpr int MAX_S = 96;  // compile-time bound of DevState::S
 
 // ---- assignCellsToGrid (jamming.cpp:527-548) ---------------------------------------------
@@ -68,63 +71,113 @@ __global__ void __launch_bounds__(RB_BLOCK) apj_bin_count_kernel(const DevState 
     atomicAdd(st.cell_count + ctl->cell_base + best, 1);
 }
 
-// ---- exclusive scan of one system's cell histogram (one block per system) -------------------
-__global__ void __launch_bounds__(SCAN_BLOCK) apj_cell_scan_kernel(const DevState st) {
-    const int sys = blockIdx.x;
+// ---- exclusive scan of every stale system's cell histogram, three short kernels -------------
+// chunk sums (SCAN_CHUNK cells per block) -> per-system scan of the chunk sums -> in-chunk scan.
+// Block-wide exclusive scan of SCAN_ITEMS values per thread; returns the block total.
+__device__ __forceinline__ int block_scan_exclusive(int (&v)[SCAN_ITEMS], int* s_warp) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) tsum += v[k];
+    int inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    int run = (wid ? s_warp[wid - 1] : 0) + inc - tsum;
+    const int total = s_warp[SCAN_BLOCK / 32 - 1];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { const int c = v[k]; v[k] = run; run += c; }
+    return total;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) apj_scan_chunk_sums_kernel(const DevState st, const int chunks) {
+    const int sys = blockIdx.y;
     const SysCtl* __restrict__ ctl = st.ctl + sys;
     if (!ctl->stale) return;
     const int nbox = ctl->nbox;
+    const int first = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+    if (blockIdx.x * SCAN_CHUNK >= nbox) return;
+    const int* __restrict__ count = st.cell_count + ctl->cell_base;
+    int tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) tsum += (first + k < nbox) ? count[first + k] : 0;
+    __shared__ int s_warp[SCAN_BLOCK / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = tsum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int w = s_warp[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if (threadIdx.x == 0) st.chunk_sums[(long long)sys * chunks + blockIdx.x] = w;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) apj_scan_chunk_offsets_kernel(const DevState st, const int chunks) {
+    const int sys = blockIdx.x;
+    const SysCtl* __restrict__ ctl = st.ctl + sys;
+    if (!ctl->stale) return;
+    const int used = (ctl->nbox + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    int* __restrict__ sums = st.chunk_sums + (long long)sys * chunks;
+    __shared__ int s_warp[SCAN_BLOCK / 32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = sys * st.N;   // absolute particle index of the system's first slot
+    __syncthreads();
+    for (int base = 0; base < used; base += SCAN_BLOCK * SCAN_ITEMS) {
+        int v[SCAN_ITEMS];
+        const int first = base + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (first + k < used) ? sums[first + k] : 0;
+        const int carry = s_carry;
+        const int total = block_scan_exclusive(v, s_warp);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) if (first + k < used) sums[first + k] = carry + v[k];
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) apj_scan_cells_kernel(const DevState st, const int chunks) {
+    const int sys = blockIdx.y;
+    const SysCtl* __restrict__ ctl = st.ctl + sys;
+    if (!ctl->stale) return;
+    const int nbox = ctl->nbox;
+    if (blockIdx.x * SCAN_CHUNK >= nbox) return;
     int* __restrict__ count = st.cell_count + ctl->cell_base;
     int* __restrict__ start = st.cell_start + ctl->cell_base;
     int* __restrict__ cursor = st.cell_cursor + ctl->cell_base;
     __shared__ int s_warp[SCAN_BLOCK / 32];
-    __shared__ int s_carry;
-    if (threadIdx.x == 0) s_carry = sys * st.N;  // absolute particle index of the system's first slot
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < nbox; base += SCAN_BLOCK * SCAN_ITEMS) {
-        int v[SCAN_ITEMS];
-        int tsum = 0;
-        const int first = base + threadIdx.x * SCAN_ITEMS;
+    const int first = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++) {
-            v[k] = (first + k < nbox) ? count[first + k] : 0;
-            tsum += v[k];
-        }
-        int inc = tsum;
+    for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (first + k < nbox) ? count[first + k] : 0;
+    const int off = st.chunk_sums[(long long)sys * chunks + blockIdx.x];
+    block_scan_exclusive(v, s_warp);
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += u;
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (first + k < nbox) {
+            start[first + k] = off + v[k];
+            cursor[first + k] = off + v[k];
+            count[first + k] = 0;  // leave the histogram clean for the next rebuild
         }
-        if (lane == 31) s_warp[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            int w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += u;
-            }
-            s_warp[lane] = w;  // inclusive over warps
-        }
-        __syncthreads();
-        const int carry = s_carry;
-        int run = carry + (wid ? s_warp[wid - 1] : 0) + inc - tsum;
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++) {
-            if (first + k < nbox) {
-                start[first + k] = run;
-                cursor[first + k] = run;
-                count[first + k] = 0;  // leave the histogram clean for the next rebuild
-            }
-            run += v[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == SCAN_BLOCK - 1) s_carry = carry + s_warp[SCAN_BLOCK / 32 - 1];
-        __syncthreads();
     }
-    if (threadIdx.x == 0) start[nbox] = s_carry;
+    if (blockIdx.x == 0 && threadIdx.x == 0) start[nbox] = (sys + 1) * st.N;   // every particle sits in some cell
 }
 
 __global__ void __launch_bounds__(RB_BLOCK) apj_scatter_kernel(const DevState st, const int bps) {
@@ -264,15 +317,12 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
                 } else {
                     piece_of_own = npieces; add_piece(d, npieces, slots, cs[lo], cs[hi + 1]);
                 }
-                if (dx == 0) {   // the block's own particles sit in the first piece of the middle column
-                    int off = before;
-                    (void)piece_of_own;
-                    d.own_slot = off + (g0 - d.pstart[piece_of_own]);
-                }
+                if (dx == 0)     // the block's own particles sit in the first piece of the middle column
+                    d.own_slot = 1 + before + (g0 - d.pstart[piece_of_own]);   // slots are 1-based (0 = sentinel)
             }
             d.info = npieces | (wraps << 8);           // list words are filled in by verlet_build
             tile_max = max(tile_max, slots);
-            if (slots > st.tile_cap || slots > 65535) over = 1;
+            if (slots > st.tile_cap || slots > 4094) over = 1;   // 16-bit entries hold slot * 16
             st.tiles[(long long)sys * st.maxblk + blk] = d;
         }
     }
@@ -286,95 +336,118 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
     }
 }
 
-// ---- buildVerletLists (jamming.cpp:550-585) as a full, distance-sorted list -------------------
-// Candidates are the 3x3 cells around the particle's cell; in the internal numbering
-// (cy + cx*b) each of the three columns is one contiguous run of particles unless it wraps in y.
-// Entries are stored as 16-bit slots of the block's tile (TileDesc), two per 32-bit word.
+// ---- buildVerletLists (jamming.cpp:550-585) as a full list in tile-slot form -----------------
+// Same work blocks and shared-memory tile as the step kernel: one thread issues TMA bulk copies
+// of the {x,y} pieces, then every thread walks the 3x3 cells around its particle (three runs of
+// consecutive tile slots, or nine single rows where y wraps) straight out of shared memory --
+// neighbouring lanes walk the same runs, so the reads are broadcasts. Two passes: count, then
+// write. Entries within BUILD_NEAR of the particle (the first coordination shell, which is what
+// can interact before the next rebuild moves anything by more than the skin) come first, the
+// rest after, each class in slot order: lanes of a warp then agree on the d2 < rn2 branch at
+// almost every list position, and consecutive lanes read nearby slots. The pair SET is what the
+// reference defines (d2 < rs2); the order inside a list is ours.
+constexpr double BUILD_NEAR2 = 3.15 * 3.15;   // rn + half the skin, squared
+
+template <bool WRAP, class F>
+__device__ __forceinline__ void for_each_candidate(const TileDesc& sd, const int* __restrict__ start, const int b, const int cx,
+                                                   const int cy, const double2* __restrict__ sXY, const int own,
+                                                   const double2 me, const double L, const double Lh, const double rs2, F&& f) {
+    auto run = [&](int a, int e) {
+        if (e <= a) return;
+        const int s0 = apj_slot_of(sd, a);
+        for (int s = s0; s < s0 + (e - a); s++) {
+            if (s == own) continue;
+            const double2 q = sXY[s];
+            double dx = q.x - me.x, dy = q.y - me.y;
+            if (WRAP) { dx = apj_wrap1(dx, L, Lh); dy = apj_wrap1(dy, L, Lh); }
+            const double d2 = apj_d2(dx, dy);
+            if (d2 < rs2) f(s, d2);
+        }
+    };
+    for (int dcx = -1; dcx <= 1; dcx++) {
+        int col = cx + dcx;
+        if (col < 0) col += b; else if (col >= b) col -= b;
+        const int* __restrict__ cs = start + col * b;
+        if (cy >= 1 && cy <= b - 2) {
+            run(cs[cy - 1], cs[cy + 2]);               // rows cy-1..cy+1 are one contiguous run
+        } else {
+            for (int dcy = -1; dcy <= 1; dcy++) {      // y wraps: row by row
+                int row = cy + dcy;
+                if (row < 0) row += b; else if (row >= b) row -= b;
+                run(cs[row], cs[row + 1]);
+            }
+        }
+    }
+}
+
+template <bool WRAP>
+__device__ __forceinline__ void build_lists(const DevState& st, SysCtl* __restrict__ ctl, const TileDesc& sd, const long long bg,
+                                            const double2* __restrict__ sXY) {
+    const int t = threadIdx.x;
+    const int g = sd.g0 + t;
+    const int gen = ctl->gen ^ 1;                      // the half reorder just wrote
+    const int* __restrict__ start = st.cell_start + ctl->cell_base;
+    const int b = ctl->b;
+    const double L = ctl->L, Lh = ctl->Lover2, rs2 = st.rs2;
+    const int own = sd.own_slot + t;
+    const double2 me = sXY[own];
+    const int c = st.BOX[gen][g];
+    const int cx = c / b, cy = c - cx * b;
+    int n_near = 0, total = 0;
+    for_each_candidate<WRAP>(sd, start, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int, double d2) {
+        total++;
+        if (d2 < BUILD_NEAR2) n_near++;
+    });
+    const int S = st.S, G = st.G;
+    const int n = min(total, S);
+    // entry e -> word e/2 -> lane (e/2) % G, that lane's word (e/2) / G, half e & 1
+    unsigned short* __restrict__ out = reinterpret_cast<unsigned short*>(st.list32 + bg * (long long)st.max_quads * st.tb * 4);
+    auto put = [&](int e, unsigned v) {
+        const int w = e >> 1, sub = w % G, kk = w / G;
+        out[(((size_t)(kk >> 2) * st.tb + t * G + sub) * 4 + (kk & 3)) * 2 + (e & 1)] = (unsigned short)v;
+    };
+    int c_near = 0, c_far = n_near;
+    for_each_candidate<WRAP>(sd, start, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int s, double d2) {
+        const int e = (d2 < BUILD_NEAR2) ? c_near++ : c_far++;
+        if (e < S) put(e, (unsigned)s << 4);
+    });
+    if (n & 1) put(n, 0u);                             // pad the last word with the sentinel
+    st.cnt[g] = n;
+    if (total > S) ctl->overflow |= 1;                 // list capacity exceeded: reported by the host
+    if (total > ctl->list_max) atomicMax(&ctl->list_max, total);
+}
+
 __global__ void __launch_bounds__(APJ_TB_MAX) apj_verlet_build_kernel(const DevState st) {
     const int sys = blockIdx.x / st.maxblk;
     const int blk = blockIdx.x - sys * st.maxblk;
     SysCtl* __restrict__ ctl = st.ctl + sys;
     if (!ctl->stale || blk >= ctl->nblk || (ctl->overflow & 2)) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* __restrict__ sXY = reinterpret_cast<double2*>(smem_raw);   // slot 0 unused here (slots are 1-based)
     __shared__ TileDesc sd;
-    __shared__ int s_lwords;
+    __shared__ __align__(8) unsigned long long s_bar;
     const long long bg = (long long)sys * st.maxblk + blk;
     if (threadIdx.x < 16) reinterpret_cast<int*>(&sd)[threadIdx.x] = reinterpret_cast<const int*>(st.tiles + bg)[threadIdx.x];
-    if (threadIdx.x == 0) s_lwords = 0;
+    if (threadIdx.x == 0) apj_mbar_init(&s_bar, 1);
     __syncthreads();
+    if (threadIdx.x == 0) {
+        const int npieces = sd.info & 0xff;
+        const double2* __restrict__ P = st.XY[ctl->cur ^ 1];           // the half reorder just wrote
+        int slots = 0;
+        for (int p = 0; p < npieces; p++) slots += sd.plen[p];
+        apj_mbar_expect_tx(&s_bar, (unsigned)slots * 16u);
+        int off = 1;
+        for (int p = 0; p < npieces; p++) {
+            apj_bulk_g2s(sXY + off, P + sd.pstart[p], (unsigned)sd.plen[p] * 16u, &s_bar);
+            off += sd.plen[p];
+        }
+    }
+    unsigned dep = 0;
+    apj_mbar_wait(&s_bar, 0, dep);
     if (threadIdx.x < sd.n) {
-    const int g = sd.g0 + threadIdx.x;
-    const int cur = ctl->cur ^ 1, gen = ctl->gen ^ 1;  // the halves reorder just wrote
-    const double2* __restrict__ P = st.XY[cur];
-    const int* __restrict__ idv = st.ID[gen];
-    const int* __restrict__ start = st.cell_start + ctl->cell_base;
-    const int b = ctl->b;
-    const double L = ctl->L, Lh = ctl->Lover2, rs2 = st.rs2;
-    const double2 me = P[g];
-    const int c = st.BOX[gen][g];
-    const int cx = c / b, cy = c - cx * b;
-
-    double kd[MAX_S];
-    int kj[MAX_S];
-    int n = 0, total = 0;
-    const int S = st.S;
-
-    for (int dcx = -1; dcx <= 1; dcx++) {
-        int col = cx + dcx;
-        if (col < 0) col += b; else if (col >= b) col -= b;
-        // rows cy-1..cy+1 of this column: one run, or split where y wraps
-        int r0[3], r1[3], nr;
-        if (cy >= 1 && cy <= b - 2) {
-            r0[0] = start[col * b + cy - 1]; r1[0] = start[col * b + cy + 2]; nr = 1;
-        } else {
-            nr = 3;
-            for (int dcy = -1; dcy <= 1; dcy++) {
-                int row = cy + dcy;
-                if (row < 0) row += b; else if (row >= b) row -= b;
-                r0[dcy + 1] = start[col * b + row]; r1[dcy + 1] = start[col * b + row + 1];
-            }
-        }
-        for (int r = 0; r < nr; r++) {
-            for (int j = r0[r]; j < r1[r]; j++) {
-                if (j == g) continue;
-                const double2 pj = P[j];
-                const double dx = apj_wrap1(pj.x - me.x, L, Lh);
-                const double dy = apj_wrap1(pj.y - me.y, L, Lh);
-                const double d2 = apj_d2(dx, dy);
-                if (d2 < rs2) {
-                    total++;
-                    // insert into the list kept sorted by (d2, id)
-                    const int idj = idv[j];
-                    int q = n - 1;
-                    if (n == S) {   // full: drop the farthest (flagged as overflow below)
-                        if (!(d2 < kd[q] || (d2 == kd[q] && idj < idv[kj[q]]))) continue;
-                        q--;
-                    } else {
-                        n++;
-                    }
-                    while (q >= 0 && (kd[q] > d2 || (kd[q] == d2 && idv[kj[q]] > idj))) {
-                        kd[q + 1] = kd[q]; kj[q + 1] = kj[q]; q--;
-                    }
-                    kd[q + 1] = d2; kj[q + 1] = j;
-                }
-            }
-        }
+        if ((sd.info >> 8) & 1) build_lists<true>(st, ctl, sd, bg, sXY);
+        else build_lists<false>(st, ctl, sd, bg, sXY);
     }
-    // word w of this particle -> [w / G][p * G + w % G] of the block's [round][tb] array
-    const int G = st.G;
-    unsigned* __restrict__ out = st.list32 + bg * (long long)st.max_rounds * st.tb + threadIdx.x * G;
-    for (int k = 0; k < n; k += 2) {
-        const unsigned lo = (unsigned)apj_slot_of(sd, kj[k]) & 0xffffu;
-        const unsigned hi = (k + 1 < n) ? ((unsigned)apj_slot_of(sd, kj[k + 1]) & 0xffffu) : 0u;
-        const int w = k >> 1;
-        out[(w / G) * st.tb + (w % G)] = lo | (hi << 16);
-    }
-    st.cnt[g] = n;
-    if (total > S) ctl->overflow |= 1;
-    if (total > ctl->list_max) atomicMax(&ctl->list_max, total);
-    atomicMax(&s_lwords, (n + 1) / 2);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) st.tiles[bg].info = sd.info | (s_lwords << 16);
 }
 
 __global__ void apj_finish_rebuild_kernel(const DevState st) {
@@ -403,15 +476,25 @@ void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nb
     const int bps = (st.N + RB_BLOCK - 1) / RB_BLOCK;
     const int grid = st.n_sys * bps;
     apj_bin_count_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
-    apj_cell_scan_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st);
+    const int chunks = (max_nbox + SCAN_CHUNK - 1) / SCAN_CHUNK;       // == DevState::scan_chunks
+    dim3 gc(chunks, st.n_sys);
+    apj_scan_chunk_sums_kernel<<<gc, SCAN_BLOCK, 0, l.stream>>>(st, chunks);
+    apj_scan_chunk_offsets_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st, chunks);
+    apj_scan_cells_kernel<<<gc, SCAN_BLOCK, 0, l.stream>>>(st, chunks);
     apj_scatter_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
     dim3 gs((max_nbox + RB_BLOCK - 1) / RB_BLOCK, st.n_sys);
     apj_cell_sort_kernel<<<gs, RB_BLOCK, 0, l.stream>>>(st);
     apj_reorder_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
     apj_make_tiles_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st);
-    apj_verlet_build_kernel<<<st.n_sys * st.maxblk, st.ppb, 0, l.stream>>>(st);
+    apj_verlet_build_kernel<<<st.n_sys * st.maxblk, st.ppb, (size_t)(st.tile_cap + 1) * 16, l.stream>>>(st);
     apj_finish_rebuild_kernel<<<(st.n_sys + 63) / 64, 64, 0, l.stream>>>(st);
-    if (l.launch_counter) (*l.launch_counter) += 8;
+    if (l.launch_counter) (*l.launch_counter) += 10;
 }
 
 int apj_max_list_capacity() { return MAX_S; }
+int apj_scan_chunk_cells() { return SCAN_CHUNK; }
+int apj_configure_rebuild(const DevState& st) {
+    const int bytes = (st.tile_cap + 1) * 16;
+    if (bytes <= 48 * 1024) return 0;
+    return cudaFuncSetAttribute(apj_verlet_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : -1;
+}

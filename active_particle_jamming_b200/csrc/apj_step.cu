@@ -32,17 +32,33 @@ namespace {
 
 struct PairAcc { double Fx, Fy, ax, ay; };
 
-// one neighbour: reference jamming.cpp:633-662 seen from particle i (gather form)
+// shared-state-space loads by 32-bit address (keeps the sweep free of generic->shared address
+// arithmetic; the addresses derive from a register the mbarrier wait "produces", so the compiler
+// cannot hoist them above the wait)
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// one neighbour: reference jamming.cpp:633-662 seen from particle i (gather form). `off` is the
+// byte offset of the neighbour's 16-byte tile slot; offset 0 is the sentinel slot, parked at
+// (1e300, 1e300) so that it fails the d2 < rn2 test like any far particle.
 template <bool WRAP>
-__device__ __forceinline__ void pair_term(PairAcc& a, const double2 me, const double Ri, const unsigned slot,
-                                          const double2* __restrict__ sXY, const double2* __restrict__ sCS,
-                                          const double2* __restrict__ sRR, const double L, const double Lh, const double rn2) {
-    const double2 q = sXY[slot];
+__device__ __forceinline__ void pair_term(PairAcc& a, const double2 me, const double Ri, const unsigned off,
+                                          const unsigned sXY, const unsigned dCS, const unsigned dRR,
+                                          const double L, const double Lh, const double rn2) {
+    const double2 q = lds_f64x2(sXY + off);
     double dx = q.x - me.x, dy = q.y - me.y;
     if (WRAP) { dx = apj_wrap1(dx, L, Lh); dy = apj_wrap1(dy, L, Lh); }   // delta_norm (:872-880)
     const double d2 = apj_d2(dx, dy);
     if (d2 < rn2) {                                   // they're neighbours (:637)
-        const double sumR = Ri + sRR[slot].x;
+        const double sumR = Ri + lds_f64(sXY + dRR + off);
         if (d2 < sumR * sumR) {                       // they also overlap (:641)
             // overlap = sumR / sqrt(d2) - 1 (:643), evaluated as sumR * rsqrt(d2) - 1: rsqrt is
             // correct to 1 ulp, so the quotient differs from the reference's by <= ~2 ulp
@@ -51,32 +67,40 @@ __device__ __forceinline__ void pair_term(PairAcc& a, const double2 me, const do
             a.Fx -= overlap * dx;
             a.Fy -= overlap * dy;
         }
-        const double2 cs = sCS[slot];
+        const double2 cs = lds_f64x2(sXY + dCS + off);
         a.ax += cs.x;                                 // add up orientations of neighbours (:659-660)
         a.ay += cs.y;
     }
 }
 
-template <int TB, int G, bool WRAP>
-__device__ __forceinline__ void sweep(PairAcc& acc, const int rounds, const int srounds, const int n, const int sub,
-                                      const unsigned* __restrict__ sL, const unsigned* __restrict__ gL,
-                                      const double2 me, const double Ri, const double2* __restrict__ sXY,
-                                      const double2* __restrict__ sCS, const double2* __restrict__ sRR,
-                                      const double L, const double Lh, const double rn2) {
-#pragma unroll 2
-    for (int i = 0; i < srounds; i++) {               // rows staged in shared memory
-        const unsigned word = sL[i * TB + threadIdx.x];
-        const int k0 = 2 * (sub + G * i);
-        if (k0 < n) pair_term<WRAP>(acc, me, Ri, word & 0xffffu, sXY, sCS, sRR, L, Lh, rn2);
-        if (k0 + 1 < n) pair_term<WRAP>(acc, me, Ri, word >> 16, sXY, sCS, sRR, L, Lh, rn2);
-    }
-    for (int i = srounds; i < rounds; i++) {          // rare: lists longer than the staged rows
-        const int k0 = 2 * (sub + G * i);
-        if (k0 < n) {
-            const unsigned word = __ldg(gL + i * TB + threadIdx.x);
-            pair_term<WRAP>(acc, me, Ri, word & 0xffffu, sXY, sCS, sRR, L, Lh, rn2);
-            if (k0 + 1 < n) pair_term<WRAP>(acc, me, Ri, word >> 16, sXY, sCS, sRR, L, Lh, rn2);
+template <bool WRAP>
+__device__ __forceinline__ void word_terms(PairAcc& a, const double2 me, const double Ri, const unsigned word,
+                                           const unsigned sXY, const unsigned dCS, const unsigned dRR,
+                                           const double L, const double Lh, const double rn2) {
+    pair_term<WRAP>(a, me, Ri, word & 0xffffu, sXY, dCS, dRR, L, Lh, rn2);
+    pair_term<WRAP>(a, me, Ri, word >> 16, sXY, dCS, dRR, L, Lh, rn2);
+}
+
+constexpr int QREG = 3;   // list quads (4 words = 8 entries each) a thread keeps in registers
+
+// nw = list words of this lane; q[] = its first QREG quads (loaded before the tile landed);
+// gq = the lane's quad column in global memory (stride TB) for the rare longer lists
+template <int TB, bool WRAP>
+__device__ __forceinline__ void sweep(PairAcc& acc, const int nw, const uint4 (&q)[QREG], const uint4* __restrict__ gq,
+                                      const double2 me, const double Ri, const unsigned sXY, const unsigned dCS,
+                                      const unsigned dRR, const double L, const double Lh, const double rn2) {
+#pragma unroll
+    for (int j = 0; j < QREG; j++) {
+        if (4 * j < nw) {
+            word_terms<WRAP>(acc, me, Ri, q[j].x, sXY, dCS, dRR, L, Lh, rn2);
+            if (4 * j + 1 < nw) word_terms<WRAP>(acc, me, Ri, q[j].y, sXY, dCS, dRR, L, Lh, rn2);
+            if (4 * j + 2 < nw) word_terms<WRAP>(acc, me, Ri, q[j].z, sXY, dCS, dRR, L, Lh, rn2);
+            if (4 * j + 3 < nw) word_terms<WRAP>(acc, me, Ri, q[j].w, sXY, dCS, dRR, L, Lh, rn2);
         }
+    }
+    for (int k = 4 * QREG; k < nw; k++) {             // rare: more than 8*QREG entries on this lane
+        const unsigned word = __ldg(reinterpret_cast<const unsigned*>(gq + (size_t)(k >> 2) * TB) + (k & 3));
+        word_terms<WRAP>(acc, me, Ri, word, sXY, dCS, dRR, L, Lh, rn2);
     }
 }
 
@@ -103,42 +127,48 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
 
     const int cur = ctl->cur, gen = ctl->gen;
 
-    double2* __restrict__ sXY = reinterpret_cast<double2*>(smem_raw);
-    double2* __restrict__ sCS = sXY + st.tile_cap;
-    double2* __restrict__ sRR = sCS + st.tile_cap;
-    unsigned* __restrict__ sL = reinterpret_cast<unsigned*>(sRR + st.tile_cap);
-    double4* __restrict__ sAcc = reinterpret_cast<double4*>(sL + st.smem_rounds * TB);
+    // tile: slot 0 is the sentinel, slots 1.. are the concatenated pieces; three arrays of 16-byte
+    // records {x,y}, {cos,sin}, {R,1/R}, each tile_cap+1 records long
+    double2* __restrict__ sXYp = reinterpret_cast<double2*>(smem_raw);
+    double2* __restrict__ sCSp = sXYp + (st.tile_cap + 1);
+    double2* __restrict__ sRRp = sCSp + (st.tile_cap + 1);
+    double4* __restrict__ sAcc = reinterpret_cast<double4*>(sRRp + (st.tile_cap + 1));   // G > 1 only
 
     if (t < 16) reinterpret_cast<int*>(&sd)[t] = desc_word;
     if (t == 0) apj_mbar_init(&s_bar, 1);
+    if (t == 32 % TB) sXYp[0] = make_double2(1e300, 1e300);
     __syncthreads();
 
     const int npieces = sd.info & 0xff;
     const bool wraps = (sd.info >> 8) & 1;
-    const int lwords = sd.info >> 16;
-    const int rounds = (lwords + G - 1) / G;
-    const int srounds = min(rounds, st.smem_rounds);
-    const unsigned* __restrict__ gL = st.list32 + bg * (long long)st.max_rounds * TB;
 
-    if (t == 0) {   // stage the tile (<= 6 pieces x 3 arrays of 16 B elements) and the list words
+    if (t == 0) {   // stage the tile: <= 6 pieces x 3 arrays, one TMA bulk copy each
         int slots = 0;
         for (int p = 0; p < npieces; p++) slots += sd.plen[p];
-        apj_mbar_expect_tx(&s_bar, (unsigned)slots * 48u + (unsigned)srounds * (TB * 4u));
-        int off = 0;
+        apj_mbar_expect_tx(&s_bar, (unsigned)slots * 48u);
+        int off = 1;
         for (int p = 0; p < npieces; p++) {
             const unsigned bytes = (unsigned)sd.plen[p] * 16u;
-            apj_bulk_g2s(sXY + off, st.XY[cur] + sd.pstart[p], bytes, &s_bar);
-            apj_bulk_g2s(sCS + off, st.CS[cur] + sd.pstart[p], bytes, &s_bar);
-            apj_bulk_g2s(sRR + off, st.RR[gen] + sd.pstart[p], bytes, &s_bar);
+            apj_bulk_g2s(sXYp + off, st.XY[cur] + sd.pstart[p], bytes, &s_bar);
+            apj_bulk_g2s(sCSp + off, st.CS[cur] + sd.pstart[p], bytes, &s_bar);
+            apj_bulk_g2s(sRRp + off, st.RR[gen] + sd.pstart[p], bytes, &s_bar);
             off += sd.plen[p];
         }
-        if (srounds) apj_bulk_g2s(sL, gL, (unsigned)srounds * (TB * 4u), &s_bar);
     }
 
     // per-thread loads that do not depend on the tile: in flight while the TMA copies land
     const int p = t / G, sub = t - p * G;              // sweep mapping: G adjacent lanes per particle
     const bool sweeping = p < sd.n;
     const int n = sweeping ? st.cnt[sd.g0 + p] : 0;
+    const int nwords = (n + 1) >> 1;
+    const int nw = (nwords - sub + G - 1) / G;         // list words of this lane (<= 0: none)
+    const uint4* __restrict__ gq = reinterpret_cast<const uint4*>(st.list32) + bg * (long long)st.max_quads * TB + t;
+    uint4 q[QREG];
+#pragma unroll
+    for (int j = 0; j < QREG; j++) {
+        q[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (4 * j < nw) q[j] = __ldg(gq + (size_t)j * TB);
+    }
     const bool active = t < sd.n;                      // epilogue mapping: thread t <-> particle t
     const long long g = (long long)sd.g0 + (active ? t : 0);
     double2 xo = make_double2(0.0, 0.0), xr = xo;
@@ -147,16 +177,18 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     const double L = ctl->L, Lh = ctl->Lover2;
     const double rn2 = st.rn2;
 
-    apj_mbar_wait(&s_bar, 0);
+    unsigned sXY = apj_smem_addr(sXYp);
+    apj_mbar_wait(&s_bar, 0, sXY);
+    const unsigned dCS = (unsigned)(st.tile_cap + 1) * 16u, dRR = 2u * dCS;
 
     // ---- neighborInteractions ----
     PairAcc acc = {0.0, 0.0, 0.0, 0.0};
     {
-        const int own = sd.own_slot + (sweeping ? p : 0);
-        const double2 me = sXY[own];
-        const double Ri = sRR[own].x;
-        if (wraps) sweep<TB, G, true>(acc, rounds, srounds, n, sub, sL, gL, me, Ri, sXY, sCS, sRR, L, Lh, rn2);
-        else sweep<TB, G, false>(acc, rounds, srounds, n, sub, sL, gL, me, Ri, sXY, sCS, sRR, L, Lh, rn2);
+        const unsigned own = (unsigned)(sd.own_slot + (sweeping ? p : 0)) * 16u;
+        const double2 me = lds_f64x2(sXY + own);
+        const double Ri = lds_f64(sXY + dRR + own);
+        if (wraps) sweep<TB, true>(acc, nw, q, gq, me, Ri, sXY, dCS, dRR, L, Lh, rn2);
+        else sweep<TB, false>(acc, nw, q, gq, me, Ri, sXY, dCS, dRR, L, Lh, rn2);
     }
     if (G > 1) {
 #pragma unroll
@@ -175,8 +207,8 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
 
     double sum_x = 0.0, sum_y = 0.0, top1 = 0.0, top2 = 0.0;
     if (active) {
-        const int own = sd.own_slot + t;
-        const double2 me = sXY[own], mcs = sCS[own], mrr = sRR[own];
+        const unsigned own = (unsigned)(sd.own_slot + t) * 16u;
+        const double2 me = lds_f64x2(sXY + own), mcs = lds_f64x2(sXY + dCS + own), mrr = lds_f64x2(sXY + dRR + own);
         const double Ri = mrr.x;
         double Fx = acc.Fx, Fy = acc.Fy, ax = acc.ax, ay = acc.ay;
         if (!ctl->no_self_once) { ax += mcs.x; ay += mcs.y; }  // self term: Cell::update left x_new = cosp (Cell.h:102-103)
@@ -331,7 +363,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
 }
 
 size_t step_smem_bytes(const DevState& st) {
-    return (size_t)st.tile_cap * 48 + (size_t)st.smem_rounds * st.tb * 4 + (size_t)st.ppb * 32;
+    return (size_t)(st.tile_cap + 1) * 48 + (st.G > 1 ? (size_t)st.ppb * 32 : 0);
 }
 
 template <int TB, int G>
