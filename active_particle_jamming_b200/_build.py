@@ -4,7 +4,8 @@ import subprocess
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "lib", "libapj_b200.so")
+# APJ_B200_LIB selects an experimental build variant by file name (tuning runs only)
+LIB = os.path.join(PKG, "lib", os.environ.get("APJ_B200_LIB", "libapj_b200.so"))
 SOURCES = ["apj_engine.cu", "apj_step.cu", "apj_rebuild.cu", "apj_observe.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               # no FMA contraction in our own arithmetic: every product/sum rounds like the reference's
@@ -22,18 +23,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    if not force and not needs_build():
+def build_library(force=False, verbose=False, defines=(), out=None):
+    out = out or LIB
+    if not force and out == LIB and not needs_build():
         return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out.stdout + out.stderr)
     if verbose:
         print(" ".join(cmd))
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -196,5 +196,6 @@ void apj_launch_step(const DevState& st, const ApjLaunch& l, const double* noise
 void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nbox, int max_b);
 int apj_configure_kernels(const DevState& st);
 int apj_configure_rebuild(const DevState& st);
+int apj_step_blocks_per_sm_limit(int tb);   // __launch_bounds__ of the step kernel
 int apj_max_list_capacity();
 int apj_scan_chunk_cells();

@@ -123,7 +123,7 @@ static int build_group_graph(apj_engine* e);
 static int blocks_per_sm(const DevState& st, int cap) {
     const size_t per_block = (size_t)(cap + 1) * 48 + (st.G > 1 ? (size_t)st.ppb * 32 : 0) + 1024 + 512;
     const int by_smem = (int)((size_t)233472 / per_block);
-    return std::max(1, std::min(by_smem, st.tb == 256 ? 4 : 8));     // register file: __launch_bounds__ of the step kernel
+    return std::max(1, std::min(by_smem, apj_step_blocks_per_sm_limit(st.tb)));   // register file: __launch_bounds__ of the step kernel
 }
 static int best_tile_cap(const DevState& st, int need) {
     need = std::min(std::max(need + need / 32 + 8, 64), 4094);

@@ -17,6 +17,7 @@
 //
 // Every kernel exits at once for systems whose ctl.stale is 0, so the chain can sit in the
 // step graph unconditionally and costs a few empty launches when no rebuild is pending.
+#include <algorithm>
 #include "apj_device.cuh"
 
 namespace {
@@ -38,15 +39,17 @@ __device__ __forceinline__ double box_centre(int i, double L, double Lh, int b) 
     return (mn + mx) / 2.;                     // :385
 }
 
+// The per-particle kernels of the chain run a fixed grid (bps blocks per system, grid-stride over
+// the system's particles): an idle chain -- the common case, it sits in every step group -- then
+// costs a few microseconds instead of retiring N / 128 empty blocks per kernel.
 __global__ void __launch_bounds__(RB_BLOCK) apj_bin_count_kernel(const DevState st, const int bps) {
     const int sys = blockIdx.x / bps;
     const SysCtl* __restrict__ ctl = st.ctl + sys;
     if (!ctl->stale) return;
-    const int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x;
-    if (i >= st.N) return;
-    const long long g = (long long)sys * st.N + i;
     const int b = ctl->b;
     const double L = ctl->L, Lh = ctl->Lover2, lp = ctl->lp;
+    for (int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x; i < st.N; i += bps * RB_BLOCK) {
+    const long long g = (long long)sys * st.N + i;
     const double2 me = st.XY[ctl->cur][g];
     const int gx = (int)floor((me.x + Lh) / lp), gy = (int)floor((me.y + Lh) / lp);
     double r2 = lp * lp * 0.25 * 2;
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(RB_BLOCK) apj_bin_count_kernel(const DevState 
     }
     st.boxnew[g] = best;
     atomicAdd(st.cell_count + ctl->cell_base + best, 1);
+    }
 }
 
 // ---- exclusive scan of every stale system's cell histogram, three short kernels -------------
@@ -184,11 +188,11 @@ __global__ void __launch_bounds__(RB_BLOCK) apj_scatter_kernel(const DevState st
     const int sys = blockIdx.x / bps;
     const SysCtl* __restrict__ ctl = st.ctl + sys;
     if (!ctl->stale) return;
-    const int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x;
-    if (i >= st.N) return;
-    const long long g = (long long)sys * st.N + i;
-    const int slot = atomicAdd(st.cell_cursor + ctl->cell_base + st.boxnew[g], 1);
-    st.perm[slot] = (int)g;
+    for (int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x; i < st.N; i += bps * RB_BLOCK) {
+        const long long g = (long long)sys * st.N + i;
+        const int slot = atomicAdd(st.cell_cursor + ctl->cell_base + st.boxnew[g], 1);
+        st.perm[slot] = (int)g;
+    }
 }
 
 // ---- per-cell sort of the slots by original particle id (CellList order, jamming.cpp:546) ----
@@ -196,18 +200,18 @@ __global__ void __launch_bounds__(RB_BLOCK) apj_cell_sort_kernel(const DevState 
     const int sys = blockIdx.y;
     const SysCtl* __restrict__ ctl = st.ctl + sys;
     if (!ctl->stale) return;
-    const int c = blockIdx.x * RB_BLOCK + threadIdx.x;
-    if (c >= ctl->nbox) return;
     const int* __restrict__ idv = st.ID[ctl->gen];
     const int* __restrict__ start = st.cell_start + ctl->cell_base;
-    const int s0 = start[c], n = start[c + 1] - s0;
-    int* __restrict__ p = st.perm + s0;
-    for (int a = 1; a < n; a++) {   // insertion sort; n is ~9 (max ~14 at phi <= 1)
-        const int pa = p[a];
-        const int ka = idv[pa];
-        int q = a - 1;
-        while (q >= 0 && idv[p[q]] > ka) { p[q + 1] = p[q]; q--; }
-        p[q + 1] = pa;
+    for (int c = blockIdx.x * RB_BLOCK + threadIdx.x; c < ctl->nbox; c += gridDim.x * RB_BLOCK) {
+        const int s0 = start[c], n = start[c + 1] - s0;
+        int* __restrict__ p = st.perm + s0;
+        for (int a = 1; a < n; a++) {   // insertion sort; n is ~9 (max ~14 at phi <= 1)
+            const int pa = p[a];
+            const int ka = idv[pa];
+            int q = a - 1;
+            while (q >= 0 && idv[p[q]] > ka) { p[q + 1] = p[q]; q--; }
+            p[q + 1] = pa;
+        }
     }
 }
 
@@ -215,10 +219,9 @@ __global__ void __launch_bounds__(RB_BLOCK) apj_reorder_kernel(const DevState st
     const int sys = blockIdx.x / bps;
     const SysCtl* __restrict__ ctl = st.ctl + sys;
     if (!ctl->stale) return;
-    const int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x;
-    if (i >= st.N) return;
-    const long long k = (long long)sys * st.N + i;
     const int cur = ctl->cur, gen = ctl->gen;
+    for (int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x; i < st.N; i += bps * RB_BLOCK) {
+    const long long k = (long long)sys * st.N + i;
     const int src = st.perm[k];
     const double2 p = st.XY[cur][src];
     st.XY[cur ^ 1][k] = p;
@@ -231,6 +234,7 @@ __global__ void __launch_bounds__(RB_BLOCK) apj_reorder_kernel(const DevState st
     st.PHI[gen ^ 1][k] = st.PHI[gen][src];
     st.ID[gen ^ 1][k] = st.ID[gen][src];
     st.BOX[gen ^ 1][k] = st.boxnew[src];
+    }
 }
 
 // ---- work decomposition: blocks of <= ppb particles inside one cell column ---------------
@@ -473,7 +477,8 @@ __global__ void apj_finish_rebuild_kernel(const DevState st) {
 
 void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nbox, int max_b) {
     (void)max_b;
-    const int bps = (st.N + RB_BLOCK - 1) / RB_BLOCK;
+    // fixed grids: ~16 blocks of 128 threads per SM in total, shared out over the systems
+    const int bps = std::max(1, std::min((st.N + RB_BLOCK - 1) / RB_BLOCK, (148 * 16 + st.n_sys - 1) / st.n_sys));
     const int grid = st.n_sys * bps;
     apj_bin_count_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
     const int chunks = (max_nbox + SCAN_CHUNK - 1) / SCAN_CHUNK;       // == DevState::scan_chunks
@@ -482,7 +487,7 @@ void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nb
     apj_scan_chunk_offsets_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st, chunks);
     apj_scan_cells_kernel<<<gc, SCAN_BLOCK, 0, l.stream>>>(st, chunks);
     apj_scatter_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
-    dim3 gs((max_nbox + RB_BLOCK - 1) / RB_BLOCK, st.n_sys);
+    dim3 gs(std::max(1, std::min((max_nbox + RB_BLOCK - 1) / RB_BLOCK, (148 * 16 + st.n_sys - 1) / st.n_sys)), st.n_sys);
     apj_cell_sort_kernel<<<gs, RB_BLOCK, 0, l.stream>>>(st);
     apj_reorder_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
     apj_make_tiles_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st);

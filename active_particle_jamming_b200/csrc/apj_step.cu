@@ -49,36 +49,42 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
 // one neighbour: reference jamming.cpp:633-662 seen from particle i (gather form). `off` is the
 // byte offset of the neighbour's 16-byte tile slot; offset 0 is the sentinel slot, parked at
 // (1e300, 1e300) so that it fails the d2 < rn2 test like any far particle.
-template <bool WRAP>
-__device__ __forceinline__ void pair_term(PairAcc& a, const double2 me, const double Ri, const unsigned off,
-                                          const unsigned sXY, const unsigned dCS, const unsigned dRR,
-                                          const double L, const double Lh, const double rn2) {
-    const double2 q = lds_f64x2(sXY + off);
-    double dx = q.x - me.x, dy = q.y - me.y;
-    if (WRAP) { dx = apj_wrap1(dx, L, Lh); dy = apj_wrap1(dy, L, Lh); }   // delta_norm (:872-880)
-    const double d2 = apj_d2(dx, dy);
-    if (d2 < rn2) {                                   // they're neighbours (:637)
-        const double sumR = Ri + lds_f64(sXY + dRR + off);
-        if (d2 < sumR * sumR) {                       // they also overlap (:641)
-            // overlap = sumR / sqrt(d2) - 1 (:643), evaluated as sumR * rsqrt(d2) - 1: rsqrt is
-            // correct to 1 ulp, so the quotient differs from the reference's by <= ~2 ulp
-            // (4e-16), far inside the 1e-12 gate, at a third of the instruction count.
-            const double overlap = sumR * rsqrt(d2) - 1;
-            a.Fx -= overlap * dx;
-            a.Fy -= overlap * dy;
-        }
-        const double2 cs = lds_f64x2(sXY + dCS + off);
-        a.ax += cs.x;                                 // add up orientations of neighbours (:659-660)
-        a.ay += cs.y;
+// interacting part of one neighbour (d2 < rn2 already established)
+__device__ __forceinline__ void pair_force(PairAcc& a, const double Ri, const double dx, const double dy, const double d2,
+                                           const unsigned at, const unsigned dCS, const unsigned dRR) {
+    const double sumR = Ri + lds_f64(at + dRR);
+    if (d2 < sumR * sumR) {                           // they also overlap (:641)
+        // overlap = sumR / sqrt(d2) - 1 (:643), evaluated as sumR * rsqrt(d2) - 1: rsqrt is
+        // correct to 1 ulp, so the quotient differs from the reference's by <= ~2 ulp
+        // (4e-16), far inside the 1e-12 gate, at a third of the instruction count.
+        const double overlap = sumR * rsqrt(d2) - 1;
+        a.Fx -= overlap * dx;
+        a.Fy -= overlap * dy;
     }
+    const double2 cs = lds_f64x2(at + dCS);
+    a.ax += cs.x;                                     // add up orientations of neighbours (:659-660)
+    a.ay += cs.y;
 }
 
+// one list word = two neighbours: reference jamming.cpp:633-662 seen from particle i (gather
+// form). Each 16-bit entry is the byte offset of the neighbour's 16-byte tile slot; offset 0 is
+// the sentinel slot, parked at (1e300, 1e300) so that it fails the d2 < rn2 test like any far
+// particle. Both position loads and distance tests are issued before either branch, so the two
+// shared-memory round trips overlap.
 template <bool WRAP>
 __device__ __forceinline__ void word_terms(PairAcc& a, const double2 me, const double Ri, const unsigned word,
                                            const unsigned sXY, const unsigned dCS, const unsigned dRR,
                                            const double L, const double Lh, const double rn2) {
-    pair_term<WRAP>(a, me, Ri, word & 0xffffu, sXY, dCS, dRR, L, Lh, rn2);
-    pair_term<WRAP>(a, me, Ri, word >> 16, sXY, dCS, dRR, L, Lh, rn2);
+    const unsigned at0 = sXY + (word & 0xffffu), at1 = sXY + (word >> 16);
+    const double2 q0 = lds_f64x2(at0), q1 = lds_f64x2(at1);
+    double dx0 = q0.x - me.x, dy0 = q0.y - me.y, dx1 = q1.x - me.x, dy1 = q1.y - me.y;
+    if (WRAP) {                                       // delta_norm (:872-880)
+        dx0 = apj_wrap1(dx0, L, Lh); dy0 = apj_wrap1(dy0, L, Lh);
+        dx1 = apj_wrap1(dx1, L, Lh); dy1 = apj_wrap1(dy1, L, Lh);
+    }
+    const double d20 = apj_d2(dx0, dy0), d21 = apj_d2(dx1, dy1);
+    if (d20 < rn2) pair_force(a, Ri, dx0, dy0, d20, at0, dCS, dRR);   // they're neighbours (:637)
+    if (d21 < rn2) pair_force(a, Ri, dx1, dy1, d21, at1, dCS, dRR);
 }
 
 constexpr int QREG = 3;   // list quads (4 words = 8 entries each) a thread keeps in registers
@@ -104,8 +110,11 @@ __device__ __forceinline__ void sweep(PairAcc& acc, const int nw, const uint4 (&
     }
 }
 
+#ifndef APJ_BLOCKS_256
+#define APJ_BLOCKS_256 4
+#endif
 template <int TB, int G, bool INJECT>
-__global__ void __launch_bounds__(TB, (TB == 256 ? 4 : 8))
+__global__ void __launch_bounds__(TB, (TB == 256 ? APJ_BLOCKS_256 : 8))
 apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const int always_full) {
     constexpr int PPB = TB / G;                        // particles per block
     constexpr int EWARPS = (PPB + 31) / 32;            // warps that run the epilogue
@@ -163,11 +172,11 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     const int nwords = (n + 1) >> 1;
     const int nw = (nwords - sub + G - 1) / G;         // list words of this lane (<= 0: none)
     const uint4* __restrict__ gq = reinterpret_cast<const uint4*>(st.list32) + bg * (long long)st.max_quads * TB + t;
-    uint4 q[QREG];
+    uint4 q[QREG];                                     // the first two quads do not wait for cnt (stale words are never swept)
 #pragma unroll
     for (int j = 0; j < QREG; j++) {
         q[j] = make_uint4(0u, 0u, 0u, 0u);
-        if (4 * j < nw) q[j] = __ldg(gq + (size_t)j * TB);
+        if (j < 2 || 4 * j < nw) q[j] = __ldg(gq + (size_t)j * TB);
     }
     const bool active = t < sd.n;                      // epilogue mapping: thread t <-> particle t
     const long long g = (long long)sd.g0 + (active ? t : 0);
@@ -176,6 +185,17 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     if (t < PPB) { xo = st.XO[gen][g]; xr = st.XR[cur][g]; id = st.ID[gen][g]; }
     const double L = ctl->L, Lh = ctl->Lover2;
     const double rn2 = st.rn2;
+    // randuni() of this step (jamming.cpp:667): depends on (id, step) only, so it is drawn while the tile is in flight
+    double u = 0.0;
+    if (t < PPB) {
+        if (INJECT) {
+            u = noise_by_id[(long long)sys * st.N + id];
+        } else {
+            const unsigned w = apj_philox_word0((unsigned)id, (unsigned)step, (unsigned)(step >> 32), (unsigned)sys,
+                                                (unsigned)st.seed, (unsigned)(st.seed >> 32));
+            u = apj_u32_to_randuni(w);
+        }
+    }
 
     unsigned sXY = apj_smem_addr(sXYp);
     apj_mbar_wait(&s_bar, 0, sXY);
@@ -221,14 +241,6 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         }
 
         // ---- phi = atan2(y_new, x_new) + CTnoise * randuni()   (jamming.cpp:667) ----
-        double u;
-        if (INJECT) {
-            u = noise_by_id[(long long)sys * st.N + id];
-        } else {
-            const unsigned w = apj_philox_word0((unsigned)id, (unsigned)step, (unsigned)(step >> 32), (unsigned)sys,
-                                                (unsigned)st.seed, (unsigned)(st.seed >> 32));
-            u = apj_u32_to_randuni(w);
-        }
         double phi = atan2(ay, ax) + ctl->CTnoise * u;
 
         // ---- Cell::update ----
@@ -390,6 +402,8 @@ void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int a
     else if (st.tb == 128 && st.G == 2) { CALL(128, 2); }                    \
     else if (st.tb == 128 && st.G == 4) { CALL(128, 4); }                    \
     else if (st.tb == 128 && st.G == 8) { CALL(128, 8); }
+
+int apj_step_blocks_per_sm_limit(int tb) { return tb == 256 ? APJ_BLOCKS_256 : 8; }
 
 int apj_configure_kernels(const DevState& st) {
 #define APJ_CFG(TB, G) return configure<TB, G>(st)
