@@ -38,5 +38,27 @@ def build_library(force=False, verbose=False, defines=(), out=None):
     return out
 
 
+HOST_SRC = os.path.join(PKG, "host", "jam", "jamming.cpp")
+HOST_BIN = os.path.join(PKG, "host", "bin", "jam")
+
+
+def build_host(force=False):
+    """The C++ jam driver (host mirror of the reference's Engine / code/classes interface), linked
+    against the CUDA library through the C ABI only."""
+    deps = [HOST_SRC, os.path.join(PKG, "..", "include", "apj_b200.h")] + [
+        os.path.join(PKG, "host", "classes", f) for f in os.listdir(os.path.join(PKG, "host", "classes"))]
+    if not force and os.path.exists(HOST_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_BIN) for d in deps):
+        return HOST_BIN
+    build_library()
+    os.makedirs(os.path.dirname(HOST_BIN), exist_ok=True)
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-o", HOST_BIN, HOST_SRC,
+           "-L" + os.path.dirname(LIB), "-lapj_b200", "-Wl,-rpath,$ORIGIN/../../lib"]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("host build failed:\n" + " ".join(cmd) + "\n" + out.stdout + out.stderr)
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))
+    print(build_host(force=True))

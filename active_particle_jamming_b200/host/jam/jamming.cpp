@@ -1,0 +1,534 @@
+// jam driver of the B200 build: same command line, same `Engine` surface and same output files as
+// the reference's code/jam/jamming.cpp (reference :43-117 Engine, :173-283 start(), :889-929 main),
+// with the hot path -- Engine::calculate_next_positions() and the observables -- delegated to the
+// CUDA library through the C ABI of include/apj_b200.h. No physics runs on the host: what stays
+// here is what the reference also does once, outside the hot loop (initial lattice, grid
+// geometry, the cadence of measurements, file output).
+//
+//   jam <fullRunID> <runID> <N> <steps> <lambda_s> <lambda_n> <rho>
+//
+// Environment (additions; the reference hard-codes these at compile time, jamming.cpp:28,36,149):
+//   APJ_OUTPUT_ROOT  root that holds local_output/ (default "./")
+//   APJ_SEED         seed of the initial condition and of the Philox noise (default: wall clock)
+//   APJ_DEVICE       CUDA device ordinal (default 0)
+#define NDIM 2
+#define PI 3.14159265
+#define PI2 6.28318531
+#define sqrt2 1.41421356
+
+#include <vector>
+#include <cmath>
+#include <ctime>
+#include <chrono>
+#include <cstdint>
+#include <cstdlib>
+#include <iostream>
+#include <random>
+#include <string>
+
+using namespace std;
+using namespace std::chrono;
+
+#include "../classes/Cell.h"
+#include "../classes/Box.h"
+#include "../classes/Print.h"
+#include "../classes/Fluctuations.h"
+#include "../classes/Correlations.h"
+#include "../../../include/apj_b200.h"
+
+const bool remote = 0;      // 0: local settings (timeAvg 10, cutoff 20), 1: cluster settings (reference :28, :147-162)
+const bool makevid = 0;     // 1: Ovito frames for the last `film` steps (reference :32)
+
+// Initial-condition randomness (reference :36-41 uses Boost mt19937 seeded from the clock; Boost is
+// not a dependency here). Radii / lattice jitter ~ N(0,1), angles ~ U[-PI,PI) on the 2^-32 lattice.
+static uint64_t g_seed = 0;
+static std::mt19937 gen;
+static std::normal_distribution<double> normdist(0, 1);
+static double randnorm() { return normdist(gen); }
+static double randuni() { return (double)gen()/4294967296.0*(PI - (-PI)) + (-PI); }
+
+struct Engine
+{
+    Engine(string, string, long int, long int, double, double, double);
+    ~Engine();
+
+    string location;
+
+    int N;
+    double CFself;
+    double CTnoise;
+    double dens;
+    string run;
+    string fullRun;
+
+    const double dt = 0.1;
+    const int nSkip = 100;
+    const int film  = nSkip*100;
+    const int fluct_int = 10;
+
+    long int totalSteps;
+    long int countdown;
+    long int t;
+    long int resetCounter;
+
+    int timeAvg;
+    int tCorrelation;
+    int cutoff;
+
+    void start();
+    void topology();
+    void initCells();
+    void assignCellsToGrid();
+    void buildVerletLists();
+    void relax();
+    bool newSkinList();
+    void calculate_next_positions();
+    void neighborInteractions();
+    void calculate_COM();
+    void saveOldPositions();
+    double calculateOrderParameter();
+    vector<double> calculateSystemOrientation();
+    void print_video(Print&);
+    double delta_norm(double);
+    double MSD();
+
+    vector<double> COM;
+    vector<double> COM0;
+    vector<double> COM_old;
+    double orderAvg, order2Avg, order4Avg;
+    double binder, variance;
+
+    vector<Cell> cell;
+    vector<Box> grid;
+    vector<vector<int>> boxPairs;       // left empty: the device derives the cell ranges within `cutoff` itself
+
+    double L;
+    double Lover2;
+    double lp;
+    int b;
+    int nbox;
+    int nboxnb;
+
+    const double rn = 2.8;
+    const double rs = 1.5*rn;
+    const double rn2 = rn*rn;
+    const double rs2 = rs*rs;
+
+    // ---- device side (additions) ----
+    apj_engine* dev = nullptr;
+    void attach_device();               // apj_create + upload of `cell`
+    void flush();                       // run the steps queued by calculate_next_positions()
+    void pull_cells();                  // refresh the host mirror `cell` from HBM
+    void pull_cell_lists();             // refresh grid[].CellList (Box::CellList, ascending particle index)
+    void pull_verlet_lists();           // refresh cell[].VerletList (half lists, partners j > i)
+
+private:
+    long int pending = 0;               // steps requested but not yet launched
+    bool lists_fresh = false;
+    long int rebuilds_seen = 0;
+    void check(int rc, const char* what);
+};
+
+void Engine::check(int rc, const char* what)
+{
+    if (rc == APJ_OK) return;
+    cout << what << " failed (" << rc << "): " << apj_last_error(dev) << endl;
+    exit(720);
+}
+
+Engine::Engine(string dir, string ID, long int n, long int steps, double l_s, double l_n, double rho)
+{
+    fullRun = dir;
+    run = ID;
+    N = n;
+    totalSteps = steps;
+    countdown = steps + 1;              // the loop in start() runs steps+1 times (reference :126,207; Q16)
+    CFself = l_s;
+    CTnoise = l_n;
+    dens = rho;
+    t = 0;
+    resetCounter = 0;
+    orderAvg = order2Avg = order4Avg = 0.0;
+    binder = variance = 0.0;
+    COM.assign(NDIM, 0.0);
+    COM0.assign(NDIM, 0.0);
+    COM_old.assign(NDIM, 0.0);
+    nboxnb = 9;
+    L = Lover2 = lp = 0.0;
+    b = nbox = 0;
+
+    const char* root = getenv("APJ_OUTPUT_ROOT");
+    location = root ? root : "./";
+    if (!location.empty() && location[location.size() - 1] != '/') location += "/";
+    if (remote == 0) { timeAvg = 10; tCorrelation = 10; cutoff = 20; }
+    else { timeAvg = 100; tCorrelation = 100; cutoff = 140; }
+}
+
+Engine::~Engine()
+{
+    if (dev) apj_destroy(dev);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side setup (done once, as in the reference)
+
+// Polydisperse radii 1 + N(0,1)/10, box from the packing fraction with the truncated PI, jittered
+// offset-row lattice, random polarity (reference initCells :285-354, 2D branch).
+void Engine::initCells()
+{
+    cell.assign(N, Cell());
+    double area = 0;
+    for (int i = 0; i < N; i++) {
+        Cell& c = cell[i];
+        c.index = i;
+        c.R = 1. + randnorm()/10;
+        c.Rinv = 1.0/c.R;
+        area += c.R*c.R;
+    }
+    L = sqrt(PI*area/dens);
+    Lover2 = L/2.0;
+
+    const int rootN = sqrt(N);
+    const double spacing = L/rootN;
+    for (int i = 0; i < N; i++) {
+        Cell& c = cell[i];
+        c.L = L; c.Lover2 = Lover2; c.dt = dt;
+        const int row = i/rootN;
+        c.x[0] = -Lover2 + spacing*(i % rootN) + randnorm()/10.;
+        c.x[1] = -Lover2 + spacing*row + randnorm()/10.;
+        if (row % 2 == 0) c.x[0] += 1.0;
+        c.theta = PI/2.0;
+        c.phi = randuni();
+        c.cosp = cos(c.phi);
+        c.sinp = sin(c.phi);
+        c.periodicAngles();
+        c.PBC();
+    }
+}
+
+// Grid of b x b boxes, b = floor(L / 2 rn), with centres and the 3x3 periodic neighbour table in
+// the reference's numbering p = i + j*b (reference topology :356-410). The device derives the same
+// b and lp from L (apj_create); the O(nbox^2) boxPairs table (:460-479) is not built.
+void Engine::topology()
+{
+    lp = 2*rn;
+    b = static_cast<int>(floor(L/lp));
+    nbox = b*b;
+    lp = L/floor(L/lp);
+    grid.assign(nbox, Box());
+    for (int j = 0; j < b; j++) {
+        for (int i = 0; i < b; i++) {
+            Box& g = grid[i + j*b];
+            g.serial_index = i + j*b;
+            g.vector_index[0] = i; g.vector_index[1] = j;
+            g.min[0] = -Lover2 + i*L/b;       g.min[1] = -Lover2 + j*L/b;
+            g.max[0] = -Lover2 + (i + 1)*L/b; g.max[1] = -Lover2 + (j + 1)*L/b;
+            for (int m = 0; m < NDIM; m++) g.center[m] = (g.min[m] + g.max[m])/2.;
+            for (int dj = -1; dj <= 1; dj++)
+                for (int di = -1; di <= 1; di++) {
+                    const int ii = (i + di + b) % b, jj = (j + dj + b) % b;
+                    g.neighbors[(di + 1) + (dj + 1)*3] = ii + jj*b;
+                }
+        }
+    }
+}
+
+void Engine::attach_device()
+{
+    apj_config cfg = {};
+    cfg.n = N;
+    cfg.n_systems = 1;
+    const char* d = getenv("APJ_DEVICE");
+    cfg.device = d ? atoi(d) : 0;
+    cfg.dt = dt; cfg.rn = rn; cfg.rs_factor = rs/rn;
+    cfg.seed = g_seed;
+    int rc = apj_create(&cfg, &L, &dev);
+    if (rc != APJ_OK) { cout << "apj_create failed (" << rc << "): " << apj_last_error(NULL) << endl; exit(720); }
+    check(apj_set_activity(dev, &CFself, &CTnoise), "apj_set_activity");
+
+    vector<double> x(N), y(N), xr(N), yr(N), x0(N), y0(N), xo(N), yo(N), R(N), phi(N), cp(N), sp(N);
+    vector<int32_t> box(N);
+    for (int i = 0; i < N; i++) {
+        const Cell& c = cell[i];
+        x[i] = c.x[0]; y[i] = c.x[1]; xr[i] = c.x_real[0]; yr[i] = c.x_real[1];
+        x0[i] = c.x0[0]; y0[i] = c.x0[1]; xo[i] = c.x_old[0]; yo[i] = c.x_old[1];
+        R[i] = c.R; phi[i] = c.phi; cp[i] = c.cosp; sp[i] = c.sinp; box[i] = c.box;
+    }
+    apj_state s = {};
+    s.x = x.data(); s.y = y.data(); s.x_real = xr.data(); s.y_real = yr.data(); s.x0 = x0.data(); s.y0 = y0.data();
+    s.x_old = xo.data(); s.y_old = yo.data(); s.R = R.data(); s.phi = phi.data(); s.cosp = cp.data(); s.sinp = sp.data();
+    s.box = box.data();
+    check(apj_upload_state(dev, &s), "apj_upload_state");          // bins and builds the lists too
+    // a fresh reference Engine starts with COM = COM_old = 0 and x_new = 0 (reference :139-141, Cell.h:75)
+    double zero[2] = {0.0, 0.0};
+    check(apj_set_com(dev, 0, zero, zero, zero), "apj_set_com");
+    check(apj_skip_self_term_once(dev, 1), "apj_skip_self_term_once");
+    lists_fresh = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hot path: thin calls into the ABI
+
+// One Euler step. Steps are queued and launched together the next time somebody looks at the
+// state (flush), so the device runs uninterrupted between two measurements.
+void Engine::calculate_next_positions()
+{
+    pending++;
+    lists_fresh = false;
+}
+
+void Engine::flush()
+{
+    if (pending > 0) {
+        check(apj_step(dev, pending), "apj_step");
+        pending = 0;
+        int64_t c[8];
+        check(apj_get_counters(dev, 0, c), "apj_get_counters");
+        rebuilds_seen = c[1] - resetCounter;
+        resetCounter = c[1];
+        double com[2], com0[2], como[2];
+        check(apj_get_com(dev, 0, com, com0, como), "apj_get_com");
+        for (int k = 0; k < NDIM; k++) { COM[k] = com[k]; COM0[k] = com0[k]; COM_old[k] = como[k]; }
+    }
+}
+
+// assignCellsToGrid + buildVerletLists are one on-device chain (counting sort + list build);
+// the pair keeps the reference's two-call protocol (start() :184-185, :245-246).
+void Engine::assignCellsToGrid()
+{
+    flush();
+    check(apj_force_rebuild(dev), "apj_force_rebuild");
+    lists_fresh = true;
+}
+
+void Engine::buildVerletLists()
+{
+    flush();
+    if (!lists_fresh) check(apj_force_rebuild(dev), "apj_force_rebuild");
+    lists_fresh = true;
+}
+
+// The skin test, the pair sweep and the COM sum are fused into the step kernel; these three keep
+// the reference's names for callers that only observe. newSkinList reports whether the steps run
+// by the last flush rebuilt the lists.
+bool Engine::newSkinList() { flush(); return rebuilds_seen > 0; }
+void Engine::neighborInteractions() { /* part of apj_step(): the fused pair sweep (csrc/apj_step.cu) */ }
+void Engine::calculate_COM() { flush(); }
+void Engine::saveOldPositions() { /* done on the device at every rebuild and by apj_mark_origin() */ }
+
+// Passive relaxation, then a linear ramp of the self-propulsion (reference relax :482-525).
+void Engine::relax()
+{
+    const long int trelax = remote ? (long int)(1000.0/dt) : 2000;
+    const long int tthermalize = remote ? 1000000 : 2000;
+    const double final_CF = CFself;
+    double zero = 0.0;
+    flush();
+    check(apj_set_activity(dev, &zero, &CTnoise), "apj_set_activity");
+    check(apj_step(dev, trelax), "apj_step");
+    check(apj_set_activity(dev, &final_CF, &CTnoise), "apj_set_activity");
+    check(apj_set_ramp(dev, tthermalize), "apj_set_ramp");
+    check(apj_step(dev, tthermalize), "apj_step");
+    check(apj_set_ramp(dev, 0), "apj_set_ramp");
+    CFself = final_CF;
+    resetCounter = 0;
+    check(apj_set_reset_counter(dev, 0, 0), "apj_set_reset_counter");
+}
+
+double Engine::calculateOrderParameter()
+{
+    flush();
+    double order = 0.0;
+    check(apj_order_orientation(dev, &order, NULL), "apj_order_orientation");
+    return order;
+}
+
+vector<double> Engine::calculateSystemOrientation()
+{
+    flush();
+    vector<double> o(NDIM, 0.0);
+    check(apj_order_orientation(dev, NULL, o.data()), "apj_order_orientation");
+    return o;
+}
+
+double Engine::MSD()
+{
+    flush();
+    double msd = 0.0;
+    check(apj_msd(dev, &msd), "apj_msd");
+    return msd;
+}
+
+double Engine::delta_norm(double delta)
+{
+    const double step = delta < -Lover2 ? L : -L;
+    while (delta < -Lover2 || delta >= Lover2) delta += step;
+    return delta;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mirrors, on request
+
+void Engine::pull_cells()
+{
+    flush();
+    vector<double> f[14];
+    for (auto& v : f) v.resize(N);
+    vector<int32_t> box(N);
+    apj_state s = {};
+    s.x = f[0].data(); s.y = f[1].data(); s.x_real = f[2].data(); s.y_real = f[3].data(); s.x0 = f[4].data(); s.y0 = f[5].data();
+    s.x_old = f[6].data(); s.y_old = f[7].data(); s.R = f[8].data(); s.phi = f[9].data(); s.cosp = f[10].data(); s.sinp = f[11].data();
+    s.vx = f[12].data(); s.vy = f[13].data(); s.box = box.data();
+    check(apj_download_state(dev, &s), "apj_download_state");
+    for (int i = 0; i < N; i++) {
+        Cell& c = cell[i];
+        c.x[0] = f[0][i]; c.x[1] = f[1][i]; c.x_real[0] = f[2][i]; c.x_real[1] = f[3][i];
+        c.x0[0] = f[4][i]; c.x0[1] = f[5][i]; c.x_old[0] = f[6][i]; c.x_old[1] = f[7][i];
+        c.phi = f[9][i]; c.cosp = f[10][i]; c.sinp = f[11][i]; c.vx = f[12][i]; c.vy = f[13][i];
+        c.x_new = c.cosp; c.y_new = c.sinp; c.box = box[i];
+    }
+}
+
+void Engine::pull_cell_lists()
+{
+    flush();
+    vector<int64_t> off(nbox + 1);
+    vector<int32_t> idx(N);
+    check(apj_get_cell_lists(dev, 0, off.data(), idx.data()), "apj_get_cell_lists");
+    for (int p = 0; p < nbox; p++) grid[p].CellList.assign(idx.begin() + off[p], idx.begin() + off[p + 1]);
+}
+
+void Engine::pull_verlet_lists()
+{
+    flush();
+    vector<int64_t> off(N + 1);
+    int64_t total = 0;
+    check(apj_get_pair_list(dev, 0, off.data(), NULL, 0, &total), "apj_get_pair_list");
+    vector<int32_t> idx(total > 0 ? total : 1);
+    check(apj_get_pair_list(dev, 0, off.data(), idx.data(), total, &total), "apj_get_pair_list");
+    for (int i = 0; i < N; i++) cell[i].VerletList.assign(idx.begin() + off[i], idx.begin() + off[i + 1]);
+}
+
+void Engine::print_video(Print& printer)
+{
+    pull_cells();
+    int first = 0;
+    for (int i = 0; i < N; i++) {
+        vector<double> velocity(3, 0.0);
+        velocity[0] = cell[i].vx;
+        velocity[1] = cell[i].vy;
+        cell[i].over = 240;             // overlap hue is not tracked on the device
+        printer.print_Ovito(first, N, i, cell[i].R, cell[i].over, cell[i].x, velocity);
+        first = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Run loop: the reference's cadence (start() :173-283) -- fluctuations every 10 steps (twice on
+// multiples of 100, Q12), order / orientation / COM / MSD every 100, correlations timeAvg times
+// per run, autocorrelation for tCorrelation steps after each of those.
+void Engine::start()
+{
+    high_resolution_clock::time_point t_begin = high_resolution_clock::now();
+
+    initCells();
+    topology();
+
+    Print printer(location, fullRun, run, N, remote);
+    Fluctuations fluct(L, totalSteps, fluct_int, dens);
+    Correlations corr(L, dens, cutoff, tCorrelation, N, CFself);
+
+    attach_device();
+    fluct.device = dev;
+    corr.device = dev;
+
+    assignCellsToGrid();
+    buildVerletLists();
+
+    relax();
+
+    check(apj_mark_origin(dev), "apj_mark_origin");       // x_real = x0 = x, COM0 = COM, saveOldPositions (:191-203)
+    pending = 0;
+
+    int corrCounter = 0;
+    const long int corr_every = totalSteps/timeAvg;
+
+    while (countdown != 0) {
+        calculate_next_positions();
+
+        if (t % fluct_int == 0) { flush(); fluct.measureFluctuations(cell, COM, printer); }
+
+        if (t % nSkip == 0) {
+            flush();
+            fluct.measureFluctuations(cell, COM, printer);
+            const double order = calculateOrderParameter();
+            vector<double> orientation = calculateSystemOrientation();
+            const double order2 = order*order;
+            orderAvg += order;
+            order2Avg += order2;
+            order4Avg += order2*order2;
+            printer.print_COM(t, COM);
+            printer.print_order(t, order);
+            printer.print_orientation(t, orientation);
+            printer.print_MSD(t, MSD());
+            if (countdown < film && makevid) print_video(printer);
+        }
+
+        if (corr_every > 0 && t % corr_every == 0 && t != 0) {
+            assignCellsToGrid();
+            buildVerletLists();
+            corr.orientation0 = calculateSystemOrientation();
+            corr.spatialCorrelations(boxPairs, grid, cell);
+            corr.velDist(cell);
+            fluct.density_distribution(cell, grid);
+            corrCounter = 0;
+        }
+
+        if (corrCounter < tCorrelation) {
+            vector<double> orient = calculateSystemOrientation();
+            corr.autocorrelation(corrCounter, orient);
+            corrCounter++;
+        }
+
+        t++;
+        countdown--;
+    }
+    flush();
+
+    orderAvg  /= (double)totalSteps/(double)nSkip;
+    order2Avg /= (double)totalSteps/(double)nSkip;
+    order4Avg /= (double)totalSteps/(double)nSkip;
+    binder = 1.0 - order4Avg/(3.0*order2Avg*order2Avg);
+    variance = order2Avg - orderAvg*orderAvg;
+
+    corr.printCorrelations(timeAvg, printer);
+    fluct.print_density_distribution(timeAvg, printer);
+
+    high_resolution_clock::time_point t_end = high_resolution_clock::now();
+    auto duration = duration_cast<seconds>(t_end - t_begin).count();
+    printer.print_summary(run, N, L, t, 1./dt, CFself, CTnoise, dens, duration, resetCounter, binder, orderAvg, variance);
+}
+
+int main(int argc, char* argv[])
+{
+    if (argc != 8) {
+        cout << "Incorrect number of arguments. Need: " << endl
+             << "- full run ID" << endl
+             << "- single run ID" << endl
+             << "- number of cells" << endl
+             << "- number of steps" << endl
+             << "- \\lambda_s" << endl
+             << "- \\lambda_n" << endl
+             << "- \\rho" << endl
+             << "Program exit status (1)" << endl;
+        return 1;
+    }
+    const char* s = getenv("APJ_SEED");
+    g_seed = s ? strtoull(s, NULL, 10)
+               : (uint64_t)duration_cast<nanoseconds>(high_resolution_clock::now().time_since_epoch()).count();
+    gen.seed((uint32_t)g_seed);
+
+    Engine engine(argv[1], argv[2], atol(argv[3]), atol(argv[4]), atof(argv[5]), atof(argv[6]), atof(argv[7]));
+    engine.start();
+    return 0;
+}

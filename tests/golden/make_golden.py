@@ -112,7 +112,65 @@ def make(name, N, rho, l_s, l_n, seed, K, cks):
     print(name, "written:", sum(v.nbytes for v in out.values()) // 1024, "KiB raw;", int(out["resets"][-1]), "skin rebuilds")
 
 
+REF = "/root/reference"
+
+
+def read_tree(root):
+    out = {}
+    for dp, _, files in os.walk(root):
+        for f in sorted(files):
+            out[os.path.relpath(os.path.join(dp, f), root)] = open(os.path.join(dp, f), "rb").read().decode("latin-1")
+    return out
+
+
+def make_print_bytes():
+    """Every Print::print_* of the REFERENCE's Print.h driven by tests/print_probe.cpp: exact bytes."""
+    import json
+    import subprocess
+    tmp = tempfile.mkdtemp()
+    exe = os.path.join(tmp, "probe")
+    subprocess.run(["g++", "-O1", "-std=c++11", "-w", "-I", os.path.join(REF, "code", "classes"),
+                    os.path.join(HERE, "..", "print_probe.cpp"), "-o", exe], check=True)
+    root = os.path.join(tmp, "out") + "/"
+    os.makedirs(root + "local_output")
+    subprocess.run([exe, root], check=True, stderr=subprocess.DEVNULL)
+    tree = read_tree(os.path.join(root, "local_output", "probe"))
+    json.dump(tree, open(os.path.join(HERE, "print_bytes.json"), "w"), indent=1, sort_keys=True)
+    print("print_bytes.json:", len(tree), "files")
+
+
+def make_run_shape(N=1024, steps=1000, l_s=0.05, l_n=0.5, rho=0.9, seed=77):
+    """One full run of the reference driver (Engine::start, jamming.cpp:173-283): the shape of every
+    output file (lines, columns, first column) + the physics scalars of its summary."""
+    import json
+    tmp = tempfile.mkdtemp()
+    RefEngine.seed(seed)
+    r = RefEngine(N, steps, l_s, l_n, rho)
+    secs = r.run_start(tmp)
+    tree = read_tree(os.path.join(tmp, "local_output", "apjref", "run0"))
+    shape = {}
+    for name, text in tree.items():
+        lines = text.split("\n")
+        assert lines[-1] == ""
+        lines = lines[:-1]
+        shape[name] = {"lines": len(lines), "columns": sorted(set(len(l.split("\t")) for l in lines)),
+                       "first_column": [l.split("\t")[0] for l in lines][:400]}
+    def col(name, k):
+        return [float(l.split("\t")[k]) for l in tree[name].split("\n")[:-1]]
+    meta = {"N": N, "steps": steps, "l_s": l_s, "l_n": l_n, "rho": rho, "seconds": secs,
+            "order_mean": float(np.mean(col("dat/order.dat", 1))), "order_std": float(np.std(col("dat/order.dat", 1))),
+            "msd_last": col("dat/MSD.dat", 1)[-1], "fluct": [col("dat/fluct.dat", 0), col("dat/fluct.dat", 1)],
+            "densDist": col("dat/densDist.dat", 1), "corr": col("dat/corr.dat", 1), "orientationCorr": col("dat/orientationCorr.dat", 1),
+            "pairCorr_sum": float(np.nansum(col("dat/pairCorr.dat", 1))), "velDist": col("dat/velDist.dat", 1),
+            "summary": tree["dat/summary.dat"]}
+    json.dump({"shape": shape, "meta": meta}, open(os.path.join(HERE, "run_shape.json"), "w"), indent=1, sort_keys=True)
+    r.close()
+    print("run_shape.json: reference run took %.2f s" % secs)
+
+
 if __name__ == "__main__":
     build()
     for c in CASES:
         make(*c)
+    make_print_bytes()
+    make_run_shape()

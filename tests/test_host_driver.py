@@ -1,0 +1,148 @@
+"""The C++ host mirror of the reference's Engine / code/classes interface
+(active_particle_jamming_b200/host): same CLI, same output tree and line formats, hot path through
+the C ABI. CPU part: Print is byte-identical to the reference's Print (golden bytes written by
+tests/golden/make_golden.py from /root/reference/code/classes/Print.h), the driver keeps the
+reference's usage/exit-code behaviour and refuses to run without a GPU. GPU part: a full run
+produces the file tree of a reference run, and its physics agrees statistically."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "active_particle_jamming_b200", "host")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def jam():
+    from active_particle_jamming_b200 import _build
+    return _build.build_host()
+
+
+def read_tree(root):
+    out = {}
+    for dp, _, files in os.walk(root):
+        for f in sorted(files):
+            out[os.path.relpath(os.path.join(dp, f), root)] = open(os.path.join(dp, f), "rb").read().decode("latin-1")
+    return out
+
+
+def test_print_is_byte_identical_to_reference(tmp_path):
+    exe = str(tmp_path / "probe")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(HOST, "classes"), os.path.join(ROOT, "tests", "print_probe.cpp"),
+                    "-o", exe], check=True)
+    root = str(tmp_path / "out") + "/"
+    os.makedirs(root + "local_output")
+    subprocess.run([exe, root], check=True)
+    got = read_tree(os.path.join(root, "local_output", "probe"))
+    want = json.load(open(os.path.join(GOLD, "print_bytes.json")))
+    assert sorted(got) == sorted(want)                       # the 14 files of Print.h:79-92
+    for name in want:
+        assert got[name] == want[name], name
+
+
+def test_usage_and_exit_code(jam):
+    r = subprocess.run([jam, "only", "three", "args"], capture_output=True, text=True)
+    assert r.returncode == 1                                 # reference jamming.cpp:901-912
+    assert r.stdout.startswith("Incorrect number of arguments. Need: \n- full run ID\n- single run ID\n- number of cells")
+    assert r.stdout.rstrip().endswith("Program exit status (1)")
+
+
+def _cuda_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_cuda_available(), reason="only meaningful without a GPU")
+def test_driver_has_no_cpu_path(jam, tmp_path):
+    env = dict(os.environ, APJ_OUTPUT_ROOT=str(tmp_path), APJ_SEED="1")
+    r = subprocess.run([jam, "full", "run0", "256", "100", "0.1", "0.5", "0.9"], capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "no CPU fallback" in r.stdout
+
+
+def test_host_classes_never_compute_the_hot_path():
+    src = open(os.path.join(HOST, "classes", "Cell.h")).read()
+    assert "exit(718)" in src                                # Cell::update aborts: the update is the kernel's epilogue
+    drv = open(os.path.join(HOST, "jam", "jamming.cpp")).read()
+    for call in ("apj_step", "apj_force_rebuild", "apj_order_orientation", "apj_msd", "apj_mark_origin"):
+        assert call in drv
+
+
+@pytest.mark.gpu
+def test_full_run_matches_reference_output_tree(jam, tmp_path):
+    g = json.load(open(os.path.join(GOLD, "run_shape.json")))
+    m = g["meta"]
+    env = dict(os.environ, APJ_OUTPUT_ROOT=str(tmp_path), APJ_SEED="20240607")
+    r = subprocess.run([jam, "apjref", "run0", str(m["N"]), str(m["steps"]), str(m["l_s"]), str(m["l_n"]), str(m["rho"])],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    tree = read_tree(os.path.join(str(tmp_path), "local_output", "apjref", "run0"))
+    assert sorted(tree) == sorted(g["shape"])
+    for name, sh in g["shape"].items():
+        lines = tree[name].split("\n")[:-1]
+        assert len(lines) == sh["lines"], name
+        assert sorted(set(len(l.split("\t")) for l in lines)) == sh["columns"], name
+        if name not in ("dat/summary2.dat", "dat/fluct.dat"):     # first column = time / abscissa / label: deterministic
+            assert [l.split("\t")[0] for l in lines][:400] == sh["first_column"], name
+
+    def col(name, k):
+        return np.array([float(l.split("\t")[k]) for l in tree[name].split("\n")[:-1]])
+    # fluct.dat: the expected areas are a deterministic function of the radius schedule (up to L, which
+    # depends on the radii drawn): the first radius is exactly 3
+    assert abs(col("dat/fluct.dat", 0)[0] - m["fluct"][0][0]) < 1e-3
+    # statistical agreement with the reference run (different random initial condition and noise stream)
+    assert abs(col("dat/order.dat", 1).mean() - m["order_mean"]) < 0.2
+    assert 0.2 * m["msd_last"] < col("dat/MSD.dat", 1)[-1] < 5 * m["msd_last"]
+    dd, dref = col("dat/densDist.dat", 1), np.array(m["densDist"])
+    assert abs(dd.sum() - dref.sum()) < 1e-9 * max(1.0, dref.sum()) + 1.5            # same number of boxes per sample (b may differ by one)
+    assert abs(np.argmax(dd) - np.argmax(dref)) <= 2
+    vd = col("dat/velDist.dat", 1)
+    assert abs(vd.sum() - np.sum(m["velDist"])) < 0.05
+    summ = tree["dat/summary.dat"].split("\n")
+    ref_summ = m["summary"].split("\n")
+    assert [l.split("\t")[0] for l in summ] == [l.split("\t")[0] for l in ref_summ]       # labels, byte for byte
+    assert summ[3] == ref_summ[3] and summ[1] == ref_summ[1]                             # steps+1 (Q16), N
+    gr = col("dat/pairCorr.dat", 1)
+    assert abs(np.nansum(gr) - m["pairCorr_sum"]) < 0.15 * m["pairCorr_sum"]
+
+
+@pytest.mark.gpu
+def test_engine_mirrors_expose_reference_state(tmp_path):
+    """Cell / Box mirrors: pull_cells, pull_cell_lists, pull_verlet_lists give the reference's views."""
+    prog = r'''
+#define main jam_main
+#include "jam/jamming.cpp"
+#undef main
+int main() {
+    gen.seed(5); g_seed = 5;
+    Engine e("mirror", "run0", 1024, 100, 0.1, 0.5, 0.9);
+    e.initCells(); e.topology(); e.attach_device();
+    e.assignCellsToGrid(); e.buildVerletLists();
+    for (int k = 0; k < 25; k++) e.calculate_next_positions();
+    e.pull_cells(); e.assignCellsToGrid(); e.buildVerletLists(); e.pull_cell_lists(); e.pull_verlet_lists();
+    long inlist = 0, pairs = 0, bad = 0;
+    for (int p = 0; p < e.nbox; p++) for (int i : e.grid[p].CellList) { inlist++; if (e.cell[i].box != p) bad++; }
+    for (int i = 0; i < e.N; i++) for (int j : e.cell[i].VerletList) {
+        pairs++;
+        double dx = e.delta_norm(e.cell[j].x[0] - e.cell[i].x[0]), dy = e.delta_norm(e.cell[j].x[1] - e.cell[i].x[1]);
+        if (!(j > i) || !(dx*dx + dy*dy < e.rs2)) bad++;
+    }
+    printf("%ld %ld %ld %d %g %g\n", inlist, pairs, bad, e.b, e.COM[0], e.calculateOrderParameter());
+    return bad != 0;
+}'''
+    src = tmp_path / "mirror.cpp"
+    src.write_text(prog)
+    from active_particle_jamming_b200 import _build
+    exe = str(tmp_path / "mirror")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", HOST, str(src), "-o", exe, "-L" + os.path.dirname(_build.LIB), "-lapj_b200",
+                    "-Wl,-rpath," + os.path.dirname(_build.LIB)], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    inlist, pairs, bad = map(int, r.stdout.split()[:3])
+    assert inlist == 1024 and bad == 0 and 7.0 < pairs / 1024 < 9.0      # half-list length ~7.9 at phi = 0.9
