@@ -125,7 +125,7 @@ int main() {
     e.initCells(); e.topology(); e.attach_device();
     e.assignCellsToGrid(); e.buildVerletLists();
     for (int k = 0; k < 25; k++) e.calculate_next_positions();
-    e.pull_cells(); e.assignCellsToGrid(); e.buildVerletLists(); e.pull_cell_lists(); e.pull_verlet_lists();
+    e.assignCellsToGrid(); e.buildVerletLists(); e.pull_cells(); e.pull_cell_lists(); e.pull_verlet_lists();
     long inlist = 0, pairs = 0, bad = 0;
     for (int p = 0; p < e.nbox; p++) for (int i : e.grid[p].CellList) { inlist++; if (e.cell[i].box != p) bad++; }
     for (int i = 0; i < e.N; i++) for (int j : e.cell[i].VerletList) {
