@@ -29,12 +29,17 @@
 
 #define APJ_TB_MAX 256      // largest thread block of the step kernel (particles per block = tb / G)
 #define APJ_MAX_PIECES 6
+#define APJ_MAX_RANKS 8     // slab mode: GPUs of one box
+// TileDesc::info bits
+#define APJ_INFO_WRAPS (1 << 8)
+#define APJ_INFO_PUSH_LEFT (1 << 9)    // slab mode: the block's particles are the left neighbour's right ghost column
+#define APJ_INFO_PUSH_RIGHT (1 << 10)  // ... the right neighbour's left ghost column
 
 struct __align__(64) TileDesc {
     int g0;         // first particle (absolute index) of the block
     int n;          // particles in the block (1..ppb)
     int own_slot;   // tile slot (1-based) of particle g0
-    int info;       // npieces | wraps << 8 | list words of the longest list << 16
+    int info;       // npieces | APJ_INFO_* flags | list words of the longest list << 16
     int pstart[APJ_MAX_PIECES];  // absolute particle index where each piece starts
     int plen[APJ_MAX_PIECES];    // particles in each piece (tile slots are the concatenation)
 };
@@ -61,11 +66,40 @@ struct __align__(128) SysCtl {
     long long step, target;
     long long reset_counter, n_rebuilds, n_discarded;
     double COM[2], COM_old[2], COM0[2];
+    // particle range of this system in the arrays: [p0, p0 + n_own). Fixed (p0 = sys*N, n_own = N) for
+    // periodic systems; in slab mode n_own changes at every rebuild (migration) and p0 = 0.
+    int p0, n_own;
+    int n_end;       // scratch of the cell scan: p0 + particles binned into owned cells
+    int col0, ncols; // slab mode: owned cell columns [col0, col0 + ncols) of the global b x b grid (periodic: 0, b)
+    int last_col_start;  // first particle of the last owned column (index of the right neighbour's ghost copy)
+    int slab_err;    // sticky: 1 peer wait timed out, 2 migrant crossed more than one slab, 4 capacity exceeded
+    int pad0;
+    unsigned long long seq[3];   // slab mode sequence numbers: step epochs, rebuild phase A, rebuild phase B
+};
+
+// ---- slab mode (one global periodic box cut into slabs of whole cell columns, one rank per GPU) ----
+// Everything a PEER writes lives in one device allocation per rank (the "arena") with the same layout
+// on every rank, so the address of any peer-visible object of rank r is
+//   peer_arena[r] + (address on this rank - arena).
+// Peers are other GPUs of the box reached over NVLink (cudaIpc mappings, one process per GPU) or, for
+// tests, other handles on the same device.
+struct __align__(16) MigRec {   // one migrating particle: every per-particle field (128 B)
+    double2 xy, cs, xr, rr, x0, xo, v;
+    double phi;
+    int id, pad;
+};
+struct __align__(16) SlabMail {
+    unsigned long long flag[3][APJ_MAX_RANKS];   // [channel][source rank]: that rank's sequence number on the channel
+    double4 part[2][APJ_MAX_RANKS];              // [epoch parity][source rank]: {sum x_real, sum y_real, top1 d2, top2 d2}
+    int inbox_count;                             // migrants pushed into `inbox` since the last rebuild
+    int ghost_n[2][2];                           // [gen parity][side] particles in the ghost column
+    int pad[3];
 };
 
 struct DevState {
-    int n_sys, N;          // systems, particles per system
-    long long ntot;        // n_sys * N
+    int n_sys, N;          // systems, particles per system (slab mode: particles of the GLOBAL box)
+    int cap;               // particle slots per system in the arrays (periodic: N; slab mode: capacity of this rank)
+    long long ntot;        // n_sys * cap
     int G;                 // lanes per particle in the sweep (1, 2, 4 or 8)
     int tb;                // threads per work block of the step kernel (128 or 256)
     int ppb;               // particles per work block = tb / G
@@ -101,7 +135,45 @@ struct DevState {
     double4* gpartials; // per group of 32 work blocks
     unsigned* gticket;  // per group arrival counter (zero between launches)
     int maxgrp;         // groups reserved per system
+    // slab mode (n_sys == 1). Array slots [cap, cap+gcap) hold the left ghost column (global column
+    // col0-1), [cap+gcap, cap+2*gcap) the right one (col0+ncols); XY, CS, RR, ID live in the arena.
+    int slab, rank, nranks, left, right;
+    int gcap, mcap;        // capacity of one ghost column / of the migration inbox
+    unsigned long long timeout_ns;   // a peer that does not show up within this time is reported, not waited for
+    char* arena;
+    char* peer_arena[APJ_MAX_RANKS];   // peer_arena[rank] == arena
+    SlabMail* mail;        // in the arena
+    MigRec* inbox;         // in the arena, mcap records
+    int* gstart;           // in the arena: [gen parity][side][b+1] row starts of the ghost columns (absolute slots)
 };
+
+template <class T>
+__device__ __forceinline__ T* apj_peer(const DevState& st, int r, T* mine) {
+    return reinterpret_cast<T*>(st.peer_arena[r] + (reinterpret_cast<char*>(mine) - st.arena));
+}
+__device__ __forceinline__ unsigned long long apj_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void apj_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long apj_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *p >= want; false on timeout
+__device__ __forceinline__ bool apj_wait_flag(const unsigned long long* p, unsigned long long want, unsigned long long timeout_ns) {
+    if (apj_ld_acquire_sys(p) >= want) return true;
+    const unsigned long long t0 = apj_globaltimer();
+    while (apj_ld_acquire_sys(p) < want) {
+        if (apj_globaltimer() - t0 > timeout_ns) return false;
+        __nanosleep(200);
+    }
+    return true;
+}
 
 // Engine::delta_norm (jamming.cpp:872-880) for |delta| < 1.5 L: one conditional add of -L or +L
 // gives the same value as the reference's while loop (k*L with k = +-1 is exact).
@@ -194,6 +266,7 @@ __device__ __forceinline__ void apj_mbar_wait(unsigned long long* bar, unsigned 
 struct ApjLaunch { cudaStream_t stream; long long* launch_counter; };
 void apj_launch_step(const DevState& st, const ApjLaunch& l, const double* noise_by_id, int always_full);
 void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nbox, int max_b);
+int apj_rebuild_chain_launches(const DevState& st);
 int apj_configure_kernels(const DevState& st);
 int apj_configure_rebuild(const DevState& st);
 int apj_step_blocks_per_sm_limit(int tb);   // __launch_bounds__ of the step kernel

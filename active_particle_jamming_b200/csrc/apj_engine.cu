@@ -34,6 +34,11 @@ struct apj_engine {
     double* d_noise = nullptr;
     ApjObsScratch obs{};
     std::string err;
+    // slab mode
+    size_t arena_bytes = 0;
+    bool peer_set[APJ_MAX_RANKS] = {};
+    bool slab_ready = false;
+    std::vector<void*> ipc_opened;
 };
 
 #define APJ_CUDA(e, call)                                                                   \
@@ -86,6 +91,7 @@ static ApjLaunch launcher(apj_engine* e, bool count) { return ApjLaunch{e->strea
 static int build_group_graph(apj_engine* e) {
     if (e->group_exec) { cudaGraphExecDestroy(e->group_exec); e->group_exec = nullptr; }
     if (e->cfg.flags & APJ_FLAG_NO_GRAPH) return APJ_OK;
+    if (e->st.slab && e->st.nranks > 1 && !e->slab_ready) return APJ_OK;   // peer addresses not known yet
     cudaGraph_t graph = nullptr;
     long long dummy = 0;
     ApjLaunch l{e->stream, &dummy};
@@ -145,6 +151,7 @@ static int set_tile_cap(apj_engine* e, int need) {
 // after pull_ctl: returns 1 if a tile overflow was repaired (caller must run the chain again)
 static int repair_tile_overflow(apj_engine* e, int* repaired) {
     *repaired = 0;
+    if (e->st.slab) return APJ_OK;   // ranks launch in lockstep: no unilateral re-launch; reported by check_overflow
     int need = 0;
     for (auto& c : e->hctl) if (c.overflow & 2) need = std::max(need, c.tile_max);
     if (!need) return APJ_OK;
@@ -162,6 +169,17 @@ static int maybe_shrink_tile_cap(apj_engine* e) {
 }
 
 static int check_overflow(apj_engine* e) {
+    if (e->st.slab && e->hctl[0].slab_err) {
+        const int f = e->hctl[0].slab_err;
+        char b[320];
+        snprintf(b, sizeof b, "slab rank %d/%d:%s%s%s", e->st.rank, e->st.nranks,
+                 (f & 1) ? " a peer rank did not arrive within the timeout;" : "",
+                 (f & 2) ? " a particle crossed more than one slab between rebuilds;" : "",
+                 (f & 4) ? " particle / ghost-column / migration capacity exceeded (recreate with a larger capacity);" : "");
+        return fail(e, (f & 4) ? APJ_E_OVERFLOW : APJ_E_STATE, b);
+    }
+    if (e->st.slab && (e->hctl[0].overflow & 2))
+        return fail(e, APJ_E_OVERFLOW, "slab mode: a work block needs a larger shared-memory tile than configured (set tile_slots)");
     for (size_t s = 0; s < e->hctl.size(); s++)
         if (e->hctl[s].overflow & 1) {
             char b[256];
@@ -172,10 +190,34 @@ static int check_overflow(apj_engine* e) {
     return APJ_OK;
 }
 
-extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** out) {
+struct SlabSpec { int on = 0, rank = 0, nranks = 1; long long cap = 0; };
+
+// carve `count` objects out of the arena (256-byte aligned); with base == nullptr only the size is computed
+template <class T>
+static void arena_take(char* base, size_t& off, T** p, size_t count) {
+    off = (off + 255) / 256 * 256;
+    if (base && p) *p = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+}
+static size_t arena_layout(DevState& st, char* base, int b) {
+    size_t off = 0;
+    const size_t n = (size_t)st.cap + 2 * (size_t)st.gcap;
+    for (int h = 0; h < 2; h++) {
+        arena_take(base, off, &st.XY[h], n); arena_take(base, off, &st.CS[h], n);
+        arena_take(base, off, &st.RR[h], n); arena_take(base, off, &st.ID[h], n);
+    }
+    arena_take(base, off, &st.gstart, (size_t)4 * (b + 1));
+    arena_take(base, off, &st.mail, 1);
+    arena_take(base, off, &st.inbox, (size_t)st.mcap);
+    return (off + 255) / 256 * 256;
+}
+
+static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& slab, apj_engine** out) {
     if (!cfg || !L || !out) return fail(nullptr, APJ_E_INVALID, "apj_create: null argument");
     if (cfg->n < 1 || cfg->n_systems < 1) return fail(nullptr, APJ_E_INVALID, "apj_create: n and n_systems must be >= 1");
     if ((long long)cfg->n * cfg->n_systems > 0x7fffffffLL) return fail(nullptr, APJ_E_INVALID, "apj_create: n*n_systems exceeds 2^31-1");
+    if (slab.on && (cfg->n_systems != 1 || slab.nranks < 1 || slab.nranks > APJ_MAX_RANKS || slab.rank < 0 || slab.rank >= slab.nranks))
+        return fail(nullptr, APJ_E_INVALID, "apj_slab_create: one system, 1 <= nranks <= 8, 0 <= rank < nranks");
     apj_engine* e = new apj_engine;
     e->cfg = *cfg;
     auto bail = [&](int code) { g_create_error = e->err; apj_destroy(e); return code; };
@@ -189,7 +231,22 @@ extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** o
     cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
 
     DevState& st = e->st;
-    st.n_sys = cfg->n_systems; st.N = (int)cfg->n; st.ntot = (long long)st.n_sys * st.N;
+    st.n_sys = cfg->n_systems; st.N = (int)cfg->n;
+    st.slab = slab.on; st.rank = slab.rank; st.nranks = slab.nranks;
+    st.left = (slab.rank + slab.nranks - 1) % slab.nranks; st.right = (slab.rank + 1) % slab.nranks;
+    st.cap = st.N;
+    st.timeout_ns = 20000000000ull;
+    if (slab.on) {
+        const double rn0 = cfg->rn > 0 ? cfg->rn : 2.8;
+        const int b0 = std::max(3, (int)floor(L[0] / (2 * rn0)));
+        const long long col = st.N / b0 + 1;                       // mean population of one cell column
+        // capacity of this rank: its share + 25 % + four columns; ghost columns / inbox: 1.5 columns + slack
+        long long cap = slab.cap > 0 ? slab.cap : (slab.nranks == 1 ? (long long)st.N : (long long)(1.25 * st.N / slab.nranks) + 4 * col + 1024);
+        st.cap = (int)std::min<long long>(cap, st.N);
+        st.gcap = (int)(col + col / 2 + 256);
+        st.mcap = st.gcap;
+    }
+    st.ntot = (long long)st.n_sys * st.cap;
     st.S = cfg->max_neighbors > 0 ? (cfg->max_neighbors + 1) / 2 * 2 : 48;
     if (st.S > apj_max_list_capacity()) { e->err = "apj_create: max_neighbors too large (<= 96)"; return bail(APJ_E_INVALID); }
     // lanes per particle: spread small systems over enough warps to hide latency (measured on B200)
@@ -219,6 +276,14 @@ extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** o
         if ((long long)c.b * c.b > 0x7ffffff0LL) { e->err = "apj_create: too many cells"; return bail(APJ_E_INVALID); }
         c.nbox = c.b * c.b;
         c.lp = c.L / floor(c.L / lp);
+        c.p0 = s * st.N; c.n_own = st.N; c.col0 = 0; c.ncols = c.b;
+        if (slab.on) {   // whole cell columns per rank: [rank*b/nranks, (rank+1)*b/nranks)
+            c.col0 = (int)((long long)slab.rank * c.b / slab.nranks);
+            c.ncols = (int)((long long)(slab.rank + 1) * c.b / slab.nranks) - c.col0;
+            if (c.ncols < 1) { e->err = "apj_slab_create: fewer cell columns than ranks"; return bail(APJ_E_INVALID); }
+            c.nbox = c.ncols * c.b;     // cells this rank owns
+            c.n_own = 0;
+        }
         c.cell_base = (int)cells;
         cells += c.nbox + 1;
         c.col_base = (int)cols;
@@ -229,10 +294,10 @@ extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** o
     }
     e->total_cells = cells;
     e->total_cols = cols;
-    st.maxblk = st.N / st.ppb + e->max_b + 1;
+    st.maxblk = st.cap / st.ppb + e->max_b + 1;
     {   // tile capacity: three columns x (block rows + 2 halo rows), sized from the mean cell occupancy
         double ppc = 0;
-        for (int s = 0; s < st.n_sys; s++) ppc = std::max(ppc, (double)st.N / e->hctl[s].nbox);
+        for (int s = 0; s < st.n_sys; s++) ppc = std::max(ppc, (double)st.N / ((double)e->hctl[s].b * e->hctl[s].b));
         const double mean = 3.0 * (st.ppb / ppc + 3.0) * ppc;   // three columns x (block rows + halo rows)
         const int want = std::min((int)(mean + 4.0 * std::sqrt(mean)) + 16, 4094);
         st.tile_cap = cfg->tile_slots > 0 ? std::min(cfg->tile_slots, 4094) : best_tile_cap(st, want);   // follows ctl.tile_max later
@@ -241,12 +306,22 @@ extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** o
     int rc = APJ_OK;
 #define A(x) if (rc == APJ_OK) rc = (x)
     A(dev_alloc(e, &st.ctl, (size_t)st.n_sys));
+    if (slab.on) {   // everything a peer writes: one allocation, same layout on every rank
+        e->arena_bytes = arena_layout(st, nullptr, e->max_b);
+        A(dev_alloc(e, &st.arena, e->arena_bytes));
+        if (rc == APJ_OK) arena_layout(st, st.arena, e->max_b);
+        st.peer_arena[st.rank] = st.arena;
+        e->peer_set[st.rank] = true;
+    }
     for (int h = 0; h < 2; h++) {
-        A(dev_alloc(e, &st.XY[h], (size_t)st.ntot)); A(dev_alloc(e, &st.CS[h], (size_t)st.ntot));
+        if (!slab.on) {
+            A(dev_alloc(e, &st.XY[h], (size_t)st.ntot)); A(dev_alloc(e, &st.CS[h], (size_t)st.ntot));
+            A(dev_alloc(e, &st.RR[h], (size_t)st.ntot)); A(dev_alloc(e, &st.ID[h], (size_t)st.ntot));
+        }
         A(dev_alloc(e, &st.XR[h], (size_t)st.ntot));
-        A(dev_alloc(e, &st.RR[h], (size_t)st.ntot));  A(dev_alloc(e, &st.X0[h], (size_t)st.ntot));
+        A(dev_alloc(e, &st.X0[h], (size_t)st.ntot));
         A(dev_alloc(e, &st.XO[h], (size_t)st.ntot)); A(dev_alloc(e, &st.V[h], (size_t)st.ntot));
-        A(dev_alloc(e, &st.PHI[h], (size_t)st.ntot)); A(dev_alloc(e, &st.ID[h], (size_t)st.ntot));
+        A(dev_alloc(e, &st.PHI[h], (size_t)st.ntot));
         A(dev_alloc(e, &st.BOX[h], (size_t)st.ntot));
     }
     A(dev_alloc(e, &st.tiles, (size_t)st.n_sys * st.maxblk));
@@ -263,21 +338,28 @@ extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** o
     st.maxgrp = (st.maxblk + 31) / 32;
     A(dev_alloc(e, &st.gpartials, (size_t)st.n_sys * st.maxgrp));
     A(dev_alloc(e, &st.gticket, (size_t)st.n_sys * st.maxgrp));
-    A(dev_alloc(e, &e->d_noise, (size_t)st.ntot));
+    A(dev_alloc(e, &e->d_noise, (size_t)st.n_sys * st.N));
     A(apj_obs_alloc(&e->obs, st, e->stream, e->allocs));
 #undef A
     if (rc != APJ_OK) return bail(rc);
     if (apj_configure_kernels(st) != 0 || apj_configure_rebuild(st) != 0) { e->err = "apj_create: cannot reserve shared memory for the tile (tile_slots too large?)"; return bail(APJ_E_CUDA); }
     if (push_ctl(e) != APJ_OK) return bail(APJ_E_CUDA);
-    if (build_group_graph(e) != APJ_OK) return bail(APJ_E_CUDA);
+    if (!slab.on || slab.nranks == 1) {      // slab mode: the graph embeds peer addresses, built by apj_slab_ready
+        if (build_group_graph(e) != APJ_OK) return bail(APJ_E_CUDA);
+    }
     *out = e;
     return APJ_OK;
+}
+
+extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** out) {
+    return create_impl(cfg, L, SlabSpec{}, out);
 }
 
 extern "C" int apj_destroy(apj_engine* e) {
     if (!e) return APJ_OK;
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->group_exec) cudaGraphExecDestroy(e->group_exec);
+    for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void* p : e->allocs) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -326,6 +408,7 @@ extern "C" int apj_upload_state(apj_engine* e, const apj_state* h) {
     if (!e || !h) return APJ_E_INVALID;
     if (!h->x || !h->y || !h->R) return fail(e, APJ_E_INVALID, "apj_upload_state: x, y and R are required");
     if (!h->phi && !(h->cosp && h->sinp)) return fail(e, APJ_E_INVALID, "apj_upload_state: phi or (cosp, sinp) required");
+    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_upload_state: slab handle, use apj_slab_upload");
     DevState& st = e->st;
     const long long n = st.ntot;
     if (int rc = pull_ctl(e)) return rc;
@@ -379,6 +462,7 @@ extern "C" int apj_upload_state(apj_engine* e, const apj_state* h) {
 extern "C" int apj_download_state(apj_engine* e, apj_state* h) {
     if (!e || !h) return APJ_E_INVALID;
     if (!e->have_state) return fail(e, APJ_E_STATE, "apj_download_state: no state uploaded");
+    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_download_state: slab handle, use apj_slab_download");
     DevState& st = e->st;
     const long long n = st.ntot;
     if (int rc = pull_ctl(e)) return rc;
@@ -443,7 +527,8 @@ extern "C" int apj_get_com(apj_engine* e, int32_t s, double* com, double* com0, 
 __global__ void apj_mark_origin_kernel(const DevState st) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= st.ntot) return;
-    const SysCtl* ctl = st.ctl + (int)(g / st.N);
+    const SysCtl* ctl = st.ctl + (int)(g / st.cap);
+    if (g - ctl->p0 >= ctl->n_own) return;
     const double2 x = st.XY[ctl->cur][g];
     st.XR[ctl->cur][g] = x;     // x_real = x   (jamming.cpp:193-196)
     st.X0[ctl->gen][g] = x;     // x0 = x
@@ -507,7 +592,7 @@ extern "C" int apj_step_injected(apj_engine* e, const double* noise) {
     if (!e || !noise) return APJ_E_INVALID;
     if (!e->have_state) return fail(e, APJ_E_STATE, "apj_step_injected: no state uploaded");
     DevState& st = e->st;
-    APJ_CUDA(e, cudaMemcpyAsync(e->d_noise, noise, sizeof(double) * st.ntot, cudaMemcpyHostToDevice, e->stream));
+    APJ_CUDA(e, cudaMemcpyAsync(e->d_noise, noise, sizeof(double) * st.n_sys * st.N, cudaMemcpyHostToDevice, e->stream));
     apj_add_target_kernel<<<(st.n_sys + 63) / 64, 64, 0, e->stream>>>(st.ctl, st.n_sys, 1);
     e->launches++;
     ApjLaunch l = launcher(e, true);
@@ -586,7 +671,8 @@ extern "C" int apj_list_stats(apj_engine* e, int32_t s, int64_t* out2) {
     DevState& st = e->st;
     unsigned long long* d = reinterpret_cast<unsigned long long*>(e->obs.d_hist);
     APJ_CUDA(e, cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), e->stream));
-    apj_list_stats_kernel<<<296, 256, 0, e->stream>>>(st.cnt + (long long)s * st.N, st.N, d);
+    if (int rc = pull_ctl(e)) return rc;
+    apj_list_stats_kernel<<<296, 256, 0, e->stream>>>(st.cnt + e->hctl[s].p0, e->hctl[s].n_own, d);
     e->launches++;
     unsigned long long h[2];
     APJ_CUDA(e, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, e->stream));
@@ -598,6 +684,7 @@ extern "C" int apj_list_stats(apj_engine* e, int32_t s, int64_t* out2) {
 extern "C" int apj_get_pair_list(apj_engine* e, int32_t s, int64_t* offsets, int32_t* idx, int64_t cap, int64_t* total) {
     if (!e || s < 0 || s >= e->st.n_sys || !total) return APJ_E_INVALID;
     if (!e->have_state) return fail(e, APJ_E_STATE, "apj_get_pair_list: no state uploaded");
+    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_get_pair_list: slab handle, use apj_slab_get_pairs");
     DevState& st = e->st;
     if (int rc = pull_ctl(e)) return rc;
     const SysCtl& c = e->hctl[s];
@@ -649,6 +736,7 @@ extern "C" int apj_get_pair_list(apj_engine* e, int32_t s, int64_t* offsets, int
 extern "C" int apj_get_cell_lists(apj_engine* e, int32_t s, int64_t* offsets, int32_t* idx) {
     if (!e || s < 0 || s >= e->st.n_sys || !offsets || !idx) return APJ_E_INVALID;
     if (!e->have_state) return fail(e, APJ_E_STATE, "apj_get_cell_lists: no state uploaded");
+    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_get_cell_lists: not available on a slab handle");
     DevState& st = e->st;
     if (int rc = pull_ctl(e)) return rc;
     const SysCtl& c = e->hctl[s];
@@ -691,6 +779,7 @@ extern "C" int apj_fluct_area(apj_engine* e, const double* radius, double* area)
 extern "C" int apj_spatial_correlations(apj_engine* e, double cutoff, double* counts, double* ori, double* vel, double* pair) {
     APJ_NEED_STATE("apj_spatial_correlations");
     if (!(cutoff > 0) || !counts || !ori || !vel || !pair) return APJ_E_INVALID;
+    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_spatial_correlations: not available on a slab handle (needs a halo of the cutoff width)");
     // nc*dr_c must not exceed the cutoff, or the reference's boxPairs filter (jamming.cpp:460-479)
     // would decide membership of the last bin; its own settings (20, 140) are multiples of 2.
     if (std::fmod(cutoff, 2.0) != 0.0) return fail(e, APJ_E_INVALID, "apj_spatial_correlations: cutoff must be a multiple of dr_c = 2");
@@ -755,4 +844,201 @@ extern "C" int apj_time_step_kernel(apj_engine* e, int64_t n, float* mean_ms, in
         }
     }
     return check_overflow(e);
+}
+
+// ---- slab mode: one global periodic box over the GPUs of a node (BASELINE config 4) ----
+extern "C" int apj_slab_create(const apj_config* cfg, double L, int32_t rank, int32_t nranks, int64_t capacity, apj_engine** out) {
+    SlabSpec sp;
+    sp.on = 1; sp.rank = rank; sp.nranks = nranks; sp.cap = capacity;
+    return create_impl(cfg, &L, sp, out);
+}
+
+extern "C" int apj_slab_info(apj_engine* e, int64_t* o) {
+    if (!e || !o || !e->st.slab) return APJ_E_INVALID;
+    if (int rc = pull_ctl(e)) return rc;
+    const SysCtl& c = e->hctl[0];
+    o[0] = e->st.rank; o[1] = e->st.nranks; o[2] = c.col0; o[3] = c.ncols; o[4] = e->st.cap; o[5] = e->st.gcap;
+    o[6] = c.n_own; o[7] = (int64_t)e->arena_bytes;
+    return APJ_OK;
+}
+
+extern "C" int apj_slab_export(apj_engine* e, void* handle64, uint64_t* local_ptr) {
+    if (!e || !e->st.slab) return APJ_E_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (handle64) {
+        cudaIpcMemHandle_t h;
+        APJ_CUDA(e, cudaIpcGetMemHandle(&h, e->st.arena));
+        memcpy(handle64, &h, sizeof h);
+    }
+    if (local_ptr) *local_ptr = (uint64_t)(uintptr_t)e->st.arena;
+    return APJ_OK;
+}
+
+extern "C" int apj_slab_connect(apj_engine* e, int32_t peer, const void* handle64, uint64_t same_process_ptr, int32_t peer_device) {
+    if (!e || !e->st.slab || peer < 0 || peer >= e->st.nranks) return APJ_E_INVALID;
+    if (peer == e->st.rank) return APJ_OK;
+    APJ_CUDA(e, cudaSetDevice(e->cfg.device));
+    if (same_process_ptr) {          // peer handle lives in this process (tests: same device; or another device of the node)
+        if (peer_device >= 0 && peer_device != e->cfg.device) {
+            int can = 0;
+            APJ_CUDA(e, cudaDeviceCanAccessPeer(&can, e->cfg.device, peer_device));
+            if (!can) return fail(e, APJ_E_CUDA, "apj_slab_connect: no peer access between the two devices");
+            cudaError_t s = cudaDeviceEnablePeerAccess(peer_device, 0);
+            if (s != cudaSuccess && s != cudaErrorPeerAccessAlreadyEnabled) APJ_CUDA(e, s);
+            cudaGetLastError();
+        }
+        e->st.peer_arena[peer] = reinterpret_cast<char*>((uintptr_t)same_process_ptr);
+    } else {
+        if (!handle64) return APJ_E_INVALID;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle64, sizeof h);
+        void* p = nullptr;
+        APJ_CUDA(e, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        e->ipc_opened.push_back(p);
+        e->st.peer_arena[peer] = reinterpret_cast<char*>(p);
+    }
+    e->peer_set[peer] = true;
+    return APJ_OK;
+}
+
+extern "C" int apj_slab_set_timeout(apj_engine* e, double seconds) {
+    if (!e || !e->st.slab || !(seconds > 0)) return APJ_E_INVALID;
+    e->st.timeout_ns = (unsigned long long)(seconds * 1e9);
+    return e->slab_ready ? build_group_graph(e) : APJ_OK;   // kernels take DevState by value
+}
+
+extern "C" int apj_slab_ready(apj_engine* e) {
+    if (!e || !e->st.slab) return APJ_E_INVALID;
+    for (int r = 0; r < e->st.nranks; r++)
+        if (!e->peer_set[r]) return fail(e, APJ_E_STATE, "apj_slab_ready: not every peer rank is connected");
+    e->slab_ready = true;
+    return build_group_graph(e);
+}
+
+extern "C" int apj_slab_upload(apj_engine* e, const apj_state* h, const int32_t* ids, int64_t n_local) {
+    if (!e || !h || !e->st.slab || n_local < 0 || (n_local > 0 && !ids)) return APJ_E_INVALID;
+    if (e->st.nranks > 1 && !e->slab_ready) return fail(e, APJ_E_STATE, "apj_slab_upload: call apj_slab_ready first");
+    if (n_local > 0 && (!h->x || !h->y || !h->R)) return fail(e, APJ_E_INVALID, "apj_slab_upload: x, y and R are required");
+    if (n_local > 0 && !h->phi && !(h->cosp && h->sinp)) return fail(e, APJ_E_INVALID, "apj_slab_upload: phi or (cosp, sinp) required");
+    DevState& st = e->st;
+    if (n_local > st.cap) return fail(e, APJ_E_OVERFLOW, "apj_slab_upload: more particles than this rank's capacity");
+    if (int rc = pull_ctl(e)) return rc;
+    const size_t n = (size_t)n_local;
+    std::vector<double2> xy(n), cs(n), rr(n), xr(n), x0(n), xo(n), v(n);
+    std::vector<double> phi(n);
+    std::vector<int> id(n), box(n, -1);
+    for (size_t g = 0; g < n; g++) {
+        xy[g] = make_double2(h->x[g], h->y[g]);
+        phi[g] = h->phi ? h->phi[g] : std::atan2(h->sinp[g], h->cosp[g]);
+        cs[g].x = h->cosp ? h->cosp[g] : std::cos(h->phi[g]);   // jamming.cpp:332-333
+        cs[g].y = h->sinp ? h->sinp[g] : std::sin(h->phi[g]);
+        xr[g] = h->x_real ? make_double2(h->x_real[g], h->y_real[g]) : xy[g];
+        x0[g] = h->x0 ? make_double2(h->x0[g], h->y0[g]) : xr[g];
+        xo[g] = h->x_old ? make_double2(h->x_old[g], h->y_old[g]) : xy[g];
+        v[g] = h->vx ? make_double2(h->vx[g], h->vy[g]) : make_double2(0.0, 0.0);
+        if (!(h->R[g] > 0.0)) return fail(e, APJ_E_INVALID, "apj_slab_upload: radii must be positive");
+        rr[g] = make_double2(h->R[g], 1.0 / h->R[g]);
+        if (ids[g] < 0 || ids[g] >= st.N) return fail(e, APJ_E_INVALID, "apj_slab_upload: particle id outside [0, N)");
+        id[g] = ids[g];
+    }
+    SysCtl& c = e->hctl[0];
+    c.cur = 0; c.gen = 0; c.stale = 1; c.save_old = 0; c.ticket = 0; c.overflow = 0; c.list_max = 0;
+    c.target = c.step; c.n_own = (int)n_local; c.p0 = 0;
+    cudaStream_t q = e->stream;
+    APJ_CUDA(e, cudaMemcpyAsync(st.XY[0], xy.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.CS[0], cs.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.XR[0], xr.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.X0[0], x0.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.XO[0], xo.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.V[0], v.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.RR[0], rr.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.PHI[0], phi.data(), n * sizeof(double), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.ID[0], id.data(), n * sizeof(int), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemcpyAsync(st.BOX[0], box.data(), n * sizeof(int), cudaMemcpyHostToDevice, q));
+    APJ_CUDA(e, cudaMemsetAsync(st.cell_count, 0, sizeof(int) * e->total_cells, q));
+    if (int rc = push_ctl(e)) return rc;
+    e->have_state = true;
+    return run_chain_now(e);   // collective: migration of misplaced particles, ghost columns, lists
+}
+
+extern "C" int apj_slab_download(apj_engine* e, apj_state* h, int32_t* ids, int64_t cap, int64_t* n_local) {
+    if (!e || !h || !e->st.slab || !n_local) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_slab_download: no state uploaded");
+    DevState& st = e->st;
+    if (int rc = pull_ctl(e)) return rc;
+    const SysCtl& c = e->hctl[0];
+    const size_t n = (size_t)c.n_own;
+    *n_local = (int64_t)n;
+    if (!ids || cap < (int64_t)n) return cap < (int64_t)n && ids ? fail(e, APJ_E_INVALID, "apj_slab_download: buffers too small") : APJ_OK;
+    std::vector<double2> xy(n), cs(n), rr(n), xr(n), x0(n), xo(n), v(n);
+    std::vector<double> phi(n);
+    std::vector<int> box(n);
+    cudaStream_t q = e->stream;
+    APJ_CUDA(e, cudaMemcpyAsync(xy.data(), st.XY[c.cur], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
+    APJ_CUDA(e, cudaMemcpyAsync(cs.data(), st.CS[c.cur], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
+    APJ_CUDA(e, cudaMemcpyAsync(xr.data(), st.XR[c.cur], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
+    APJ_CUDA(e, cudaMemcpyAsync(x0.data(), st.X0[c.gen], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
+    APJ_CUDA(e, cudaMemcpyAsync(xo.data(), st.XO[c.gen], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
+    APJ_CUDA(e, cudaMemcpyAsync(v.data(), st.V[c.gen], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
+    APJ_CUDA(e, cudaMemcpyAsync(rr.data(), st.RR[c.gen], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
+    APJ_CUDA(e, cudaMemcpyAsync(phi.data(), st.PHI[c.gen], n * sizeof(double), cudaMemcpyDeviceToHost, q));
+    APJ_CUDA(e, cudaMemcpyAsync(ids, st.ID[c.gen], n * sizeof(int), cudaMemcpyDeviceToHost, q));
+    APJ_CUDA(e, cudaMemcpyAsync(box.data(), st.BOX[c.gen], n * sizeof(int), cudaMemcpyDeviceToHost, q));
+    APJ_CUDA(e, cudaStreamSynchronize(q));
+    for (size_t g = 0; g < n; g++) {
+        if (h->x) h->x[g] = xy[g].x;           if (h->y) h->y[g] = xy[g].y;
+        if (h->cosp) h->cosp[g] = cs[g].x;     if (h->sinp) h->sinp[g] = cs[g].y;
+        if (h->x_real) h->x_real[g] = xr[g].x; if (h->y_real) h->y_real[g] = xr[g].y;
+        if (h->x0) h->x0[g] = x0[g].x;         if (h->y0) h->y0[g] = x0[g].y;
+        if (h->x_old) h->x_old[g] = xo[g].x;   if (h->y_old) h->y_old[g] = xo[g].y;
+        if (h->vx) h->vx[g] = v[g].x;          if (h->vy) h->vy[g] = v[g].y;
+        if (h->R) h->R[g] = rr[g].x;           if (h->phi) h->phi[g] = phi[g];
+        if (h->box) { const int bi = box[g]; h->box[g] = bi < 0 ? -1 : (bi / c.b + c.col0) + (bi % c.b) * c.b; }   // reference numbering i + j*b
+    }
+    return APJ_OK;
+}
+
+extern "C" int apj_slab_get_pairs(apj_engine* e, int32_t* pairs, int64_t cap_pairs, int64_t* total) {
+    if (!e || !e->st.slab || !total) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_slab_get_pairs: no state uploaded");
+    DevState& st = e->st;
+    if (int rc = pull_ctl(e)) return rc;
+    const SysCtl& c = e->hctl[0];
+    const size_t nall = (size_t)st.cap + 2 * (size_t)st.gcap;
+    const size_t words_per_blk = (size_t)st.max_quads * 4 * st.tb;
+    std::vector<int> id(nall), cnt(st.cap);
+    std::vector<TileDesc> tiles(c.nblk);
+    std::vector<unsigned> lst(words_per_blk * c.nblk);
+    APJ_CUDA(e, cudaMemcpyAsync(id.data(), st.ID[c.gen], nall * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaMemcpyAsync(cnt.data(), st.cnt, (size_t)st.cap * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaMemcpyAsync(tiles.data(), st.tiles, c.nblk * sizeof(TileDesc), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaMemcpyAsync(lst.data(), st.list32, lst.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    int64_t tot = 0;
+    size_t covered = 0;
+    for (int blk = 0; blk < c.nblk; blk++) {
+        const TileDesc& d = tiles[blk];
+        for (int t = 0; t < d.n; t++, covered++) {
+            const long long g = d.g0 + t;
+            if (g < 0 || g >= c.n_own) return fail(e, APJ_E_STATE, "apj_slab_get_pairs: tile outside the owned range");
+            for (int k = 0; k < cnt[g]; k++) {
+                const int wi = k >> 1, sub = wi % st.G, kk = wi / st.G;
+                const unsigned w = lst[blk * words_per_blk + ((size_t)(kk >> 2) * st.tb + (size_t)t * st.G + sub) * 4 + (kk & 3)];
+                int slot = (int)(((k & 1) ? (w >> 16) : (w & 0xffffu)) >> 4) - 1;
+                long long j = -1;
+                for (int p = 0; p < (d.info & 0xff); p++) {
+                    if (slot < d.plen[p]) { j = (long long)d.pstart[p] + slot; break; }
+                    slot -= d.plen[p];
+                }
+                if (j < 0 || j >= (long long)nall || (j >= c.n_own && j < st.cap)) return fail(e, APJ_E_STATE, "apj_slab_get_pairs: list entry outside its tile");
+                if (id[j] > id[g]) {
+                    if (pairs && tot < cap_pairs) { pairs[2 * tot] = id[g]; pairs[2 * tot + 1] = id[j]; }
+                    tot++;
+                }
+            }
+        }
+    }
+    if (covered != (size_t)c.n_own) return fail(e, APJ_E_STATE, "apj_slab_get_pairs: work blocks do not cover the owned particles");
+    *total = tot;
+    return APJ_OK;
 }

@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(OB) apj_obs_reduce_kernel(const DevState st, c
     const int sys = blockIdx.x / bps, blk = blockIdx.x - sys * bps;
     const SysCtl* __restrict__ ctl = st.ctl + sys;
     double a = 0.0, b = 0.0;
-    for (int i = blk * OB + threadIdx.x; i < st.N; i += bps * OB) {
-        const long long g = (long long)sys * st.N + i;
+    for (int i = blk * OB + threadIdx.x; i < ctl->n_own; i += bps * OB) {
+        const long long g = (long long)ctl->p0 + i;
         if (MODE == OBS_COM) {
             const double2 xr = st.XR[ctl->cur][g];
             a += xr.x; b += xr.y;
@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(OB) apj_velhist_kernel(const DevState st, cons
     __shared__ unsigned sh[100];
     for (int k = threadIdx.x; k < 100; k += OB) sh[k] = 0;
     __syncthreads();
-    for (int i = blk * OB + threadIdx.x; i < st.N; i += bps * OB) {
-        const double2 v = st.V[ctl->gen][(long long)sys * st.N + i];
+    for (int i = blk * OB + threadIdx.x; i < ctl->n_own; i += bps * OB) {
+        const double2 v = st.V[ctl->gen][(long long)ctl->p0 + i];
         const double sp = sqrt(v.x * v.x + v.y * v.y);
         const double q = floor(sp / dv[sys]);
         if (q < 100.0) { const int bin = (int)q; if (bin >= 0) atomicAdd(&sh[bin], 1u); }
@@ -196,7 +196,7 @@ int reduce2(ApjObsScratch* o, const DevState& st, cudaStream_t s, long long* lau
 }  // namespace
 
 int apj_obs_alloc(ApjObsScratch* o, const DevState& st, cudaStream_t stream, std::vector<void*>& allocs) {
-    o->blocks_per_sys = std::max(1, std::min((st.N + OB - 1) / OB, 1024));
+    o->blocks_per_sys = std::max(1, std::min((st.cap + OB - 1) / OB, 1024));
     auto A = [&](void** p, size_t bytes) {
         if (cudaMalloc(p, bytes) != cudaSuccess) return APJ_E_CUDA_OBS;
         cudaMemsetAsync(*p, 0, bytes, stream);

@@ -42,18 +42,12 @@ __device__ __forceinline__ double box_centre(int i, double L, double Lh, int b) 
 // The per-particle kernels of the chain run a fixed grid (bps blocks per system, grid-stride over
 // the system's particles): an idle chain -- the common case, it sits in every step group -- then
 // costs a few microseconds instead of retiring N / 128 empty blocks per kernel.
-__global__ void __launch_bounds__(RB_BLOCK) apj_bin_count_kernel(const DevState st, const int bps) {
-    const int sys = blockIdx.x / bps;
-    const SysCtl* __restrict__ ctl = st.ctl + sys;
-    if (!ctl->stale) return;
-    const int b = ctl->b;
-    const double L = ctl->L, Lh = ctl->Lover2, lp = ctl->lp;
-    for (int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x; i < st.N; i += bps * RB_BLOCK) {
-    const long long g = (long long)sys * st.N + i;
-    const double2 me = st.XY[ctl->cur][g];
+// returns the winning box as (column, row) of the GLOBAL grid; prev_x < 0: no previous box
+__device__ __forceinline__ int2 nearest_box(const double2 me, const double L, const double Lh, const double lp, const int b,
+                                            int prev_x, int prev_y) {
     const int gx = (int)floor((me.x + Lh) / lp), gy = (int)floor((me.y + Lh) / lp);
     double r2 = lp * lp * 0.25 * 2;
-    int best = st.BOX[ctl->gen][g];
+    int bx = prev_x, by = prev_y;
     for (int qy = gy - 1; qy <= gy + 1; qy++) {
         if (qy < 0 || qy >= b) continue;
         const double dry = me.y - box_centre(qy, L, Lh, b);
@@ -63,15 +57,104 @@ __global__ void __launch_bounds__(RB_BLOCK) apj_bin_count_kernel(const DevState 
             double d2 = 0.0;
             d2 += drx * drx;
             d2 += dry * dry;
-            if (d2 < r2) { r2 = d2; best = qy + qx * b; }  // internal numbering: columns contiguous
+            if (d2 < r2) { r2 = d2; bx = qx; by = qy; }
         }
     }
-    if (best < 0) {  // reference would index grid[-1]; clamp to the floor bin instead
-        const int cx = min(max(gx, 0), b - 1), cy = min(max(gy, 0), b - 1);
-        best = cy + cx * b;
+    if (bx < 0) {  // reference would index grid[-1]; clamp to the floor bin instead
+        bx = min(max(gx, 0), b - 1); by = min(max(gy, 0), b - 1);
     }
-    st.boxnew[g] = best;
-    atomicAdd(st.cell_count + ctl->cell_base + best, 1);
+    return make_int2(bx, by);
+}
+
+__global__ void __launch_bounds__(RB_BLOCK) apj_bin_count_kernel(const DevState st, const int bps) {
+    const int sys = blockIdx.x / bps;
+    SysCtl* __restrict__ ctl = st.ctl + sys;
+    if (!ctl->stale) return;
+    const int b = ctl->b, col0 = ctl->col0, ncols = ctl->ncols;
+    const double L = ctl->L, Lh = ctl->Lover2, lp = ctl->lp;
+    const int cur = ctl->cur, gen = ctl->gen;
+    const int n = ctl->n_own;
+    for (int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x; i < n; i += bps * RB_BLOCK) {
+        const long long g = (long long)ctl->p0 + i;
+        const double2 me = st.XY[cur][g];
+        const int prev = st.BOX[gen][g];      // internal numbering cy + (cx - col0) * b: columns contiguous
+        const int2 q = nearest_box(me, L, Lh, lp, b, prev < 0 ? -1 : prev / b + col0, prev < 0 ? -1 : prev % b);
+        const int lc = q.x - col0;
+        if (lc >= 0 && lc < ncols) {
+            const int best = q.y + lc * b;
+            st.boxnew[g] = best;
+            atomicAdd(st.cell_count + ctl->cell_base + best, 1);
+            continue;
+        }
+        // slab mode: the particle left this rank's columns -> hand the whole record to the neighbour
+        // that owns its column (a peer atomic reserves the inbox slot, a peer store fills it)
+        st.boxnew[g] = -1;
+        int dst = -1;
+        if (q.x == (col0 + b - 1) % b) dst = st.left;
+        else if (q.x == (col0 + ncols) % b) dst = st.right;
+        if (dst < 0) { ctl->slab_err |= 2; continue; }
+        MigRec r;
+        r.xy = me; r.cs = st.CS[cur][g]; r.xr = st.XR[cur][g]; r.rr = st.RR[gen][g]; r.x0 = st.X0[gen][g];
+        r.xo = st.XO[gen][g]; r.v = st.V[gen][g]; r.phi = st.PHI[gen][g]; r.id = st.ID[gen][g]; r.pad = 0;
+        const int k = atomicAdd_system(&apj_peer(st, dst, st.mail)->inbox_count, 1);
+        if (k < st.mcap) apj_peer(st, dst, st.inbox)[k] = r;
+        else ctl->slab_err |= 4;
+    }
+}
+
+// ---- slab mode: rendezvous of all ranks of the box (one warp). Everything this rank wrote into peer
+// memory in earlier kernels of its stream is complete at this kernel's start; the release store of
+// the sequence number publishes it, the acquire loads of the peers' numbers make theirs visible.
+__global__ void apj_slab_sync_kernel(const DevState st, const int ch) {
+    SysCtl* __restrict__ ctl = st.ctl;
+    if (!ctl->stale) return;
+    const int lane = threadIdx.x;
+    const unsigned long long seq = ctl->seq[ch] + 1;
+    __syncwarp();
+    __threadfence_system();
+    if (lane < st.nranks) apj_st_release_sys(&apj_peer(st, lane, st.mail)->flag[ch][st.rank], seq);
+    bool ok = true;
+    if (lane < st.nranks && !ctl->slab_err) ok = apj_wait_flag(&st.mail->flag[ch][lane], seq, st.timeout_ns);
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        ctl->seq[ch] = seq;
+        if (!ok) ctl->slab_err |= 1;
+    }
+}
+
+// particles in the arrays before the sort: owned ones + the migrants the neighbours delivered
+__device__ __forceinline__ int slab_n_src(const DevState& st, const SysCtl* ctl) {
+    if (!st.slab) return ctl->n_own;
+    const int n_in = min(__ldcg(&st.mail->inbox_count), st.mcap);
+    return min(ctl->n_own + n_in, st.cap);
+}
+
+// ---- slab mode: append the delivered migrants to the arrays and bin them ----
+__global__ void __launch_bounds__(RB_BLOCK) apj_absorb_kernel(const DevState st) {
+    SysCtl* __restrict__ ctl = st.ctl;
+    if (!ctl->stale) return;
+    const int b = ctl->b, col0 = ctl->col0, ncols = ctl->ncols;
+    const double L = ctl->L, Lh = ctl->Lover2, lp = ctl->lp;
+    const int cur = ctl->cur, gen = ctl->gen;
+    const int n_in_all = __ldcg(&st.mail->inbox_count);
+    const int n_own = ctl->n_own;
+    const int n_in = slab_n_src(st, ctl) - n_own;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (n_in_all > st.mcap || n_own + n_in_all > st.cap)) ctl->slab_err |= 4;
+    for (int k = blockIdx.x * RB_BLOCK + threadIdx.x; k < n_in; k += gridDim.x * RB_BLOCK) {
+        const MigRec r = st.inbox[k];
+        const long long g = n_own + k;
+        st.XY[cur][g] = r.xy; st.CS[cur][g] = r.cs; st.XR[cur][g] = r.xr; st.RR[gen][g] = r.rr; st.X0[gen][g] = r.x0;
+        st.XO[gen][g] = r.xo; st.V[gen][g] = r.v; st.PHI[gen][g] = r.phi; st.ID[gen][g] = r.id; st.BOX[gen][g] = -1;
+        const int2 q = nearest_box(r.xy, L, Lh, lp, b, -1, -1);
+        const int lc = q.x - col0;
+        if (lc >= 0 && lc < ncols) {
+            const int best = q.y + lc * b;
+            st.boxnew[g] = best;
+            atomicAdd(st.cell_count + ctl->cell_base + best, 1);
+        } else {           // cannot happen: the sender binned it with the same arithmetic
+            st.boxnew[g] = -1;
+            ctl->slab_err |= 2;
+        }
     }
 }
 
@@ -140,7 +223,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_scan_chunk_offsets_kernel(cons
     int* __restrict__ sums = st.chunk_sums + (long long)sys * chunks;
     __shared__ int s_warp[SCAN_BLOCK / 32];
     __shared__ int s_carry;
-    if (threadIdx.x == 0) s_carry = sys * st.N;   // absolute particle index of the system's first slot
+    if (threadIdx.x == 0) s_carry = ctl->p0;      // absolute particle index of the system's first slot
     __syncthreads();
     for (int base = 0; base < used; base += SCAN_BLOCK * SCAN_ITEMS) {
         int v[SCAN_ITEMS];
@@ -155,6 +238,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_scan_chunk_offsets_kernel(cons
         if (threadIdx.x == 0) s_carry = carry + total;
         __syncthreads();
     }
+    if (threadIdx.x == 0) st.ctl[sys].n_end = s_carry;   // one past the last binned particle
 }
 
 __global__ void __launch_bounds__(SCAN_BLOCK) apj_scan_cells_kernel(const DevState st, const int chunks) {
@@ -181,16 +265,19 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_scan_cells_kernel(const DevSta
             count[first + k] = 0;  // leave the histogram clean for the next rebuild
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) start[nbox] = (sys + 1) * st.N;   // every particle sits in some cell
+    if (blockIdx.x == 0 && threadIdx.x == 0) start[nbox] = ctl->n_end;   // every particle that stays sits in some cell
 }
 
 __global__ void __launch_bounds__(RB_BLOCK) apj_scatter_kernel(const DevState st, const int bps) {
     const int sys = blockIdx.x / bps;
     const SysCtl* __restrict__ ctl = st.ctl + sys;
     if (!ctl->stale) return;
-    for (int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x; i < st.N; i += bps * RB_BLOCK) {
-        const long long g = (long long)sys * st.N + i;
-        const int slot = atomicAdd(st.cell_cursor + ctl->cell_base + st.boxnew[g], 1);
+    const int n = slab_n_src(st, ctl);
+    for (int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x; i < n; i += bps * RB_BLOCK) {
+        const long long g = (long long)ctl->p0 + i;
+        const int c = st.boxnew[g];
+        if (c < 0) continue;               // slab mode: emigrated
+        const int slot = atomicAdd(st.cell_cursor + ctl->cell_base + c, 1);
         st.perm[slot] = (int)g;
     }
 }
@@ -220,8 +307,9 @@ __global__ void __launch_bounds__(RB_BLOCK) apj_reorder_kernel(const DevState st
     const SysCtl* __restrict__ ctl = st.ctl + sys;
     if (!ctl->stale) return;
     const int cur = ctl->cur, gen = ctl->gen;
-    for (int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x; i < st.N; i += bps * RB_BLOCK) {
-    const long long k = (long long)sys * st.N + i;
+    const int n = ctl->n_end - ctl->p0;
+    for (int i = (blockIdx.x - sys * bps) * RB_BLOCK + threadIdx.x; i < n; i += bps * RB_BLOCK) {
+    const long long k = (long long)ctl->p0 + i;
     const int src = st.perm[k];
     const double2 p = st.XY[cur][src];
     st.XY[cur ^ 1][k] = p;
@@ -234,6 +322,38 @@ __global__ void __launch_bounds__(RB_BLOCK) apj_reorder_kernel(const DevState st
     st.PHI[gen ^ 1][k] = st.PHI[gen][src];
     st.ID[gen ^ 1][k] = st.ID[gen][src];
     st.BOX[gen ^ 1][k] = st.boxnew[src];
+    }
+}
+
+// ---- slab mode: the first / last owned column becomes the left / right neighbour's ghost column ----
+// Full records of what a neighbour's sweep reads ({x,y}, {cos,sin}, {R,1/R}, id) and the row starts of
+// the column go straight into the neighbour's arrays (peer stores); between rebuilds the step kernel
+// refreshes {x,y} and {cos,sin} of the same slots from its epilogue.
+__global__ void __launch_bounds__(RB_BLOCK) apj_push_ghosts_kernel(const DevState st) {
+    SysCtl* __restrict__ ctl = st.ctl;
+    if (!ctl->stale) return;
+    const int b = ctl->b, w = ctl->ncols;
+    const int* __restrict__ start = st.cell_start + ctl->cell_base;
+    const int h = ctl->cur ^ 1, gn = ctl->gen ^ 1;       // the halves reorder just wrote
+    for (int d = 0; d < 2; d++) {
+        const int c_lo = d == 0 ? 0 : (w - 1) * b;
+        const int dst = d == 0 ? st.left : st.right;
+        const int side = d == 0 ? 1 : 0;                 // my first column is the left neighbour's RIGHT ghost
+        const int s0 = start[c_lo];
+        int n = start[c_lo + b] - s0;
+        if (n > st.gcap) { if (blockIdx.x == 0 && threadIdx.x == 0) ctl->slab_err |= 4; n = st.gcap; }
+        const long long base = (long long)st.cap + (long long)side * st.gcap;
+        double2* __restrict__ pXY = apj_peer(st, dst, st.XY[h]) + base;
+        double2* __restrict__ pCS = apj_peer(st, dst, st.CS[h]) + base;
+        double2* __restrict__ pRR = apj_peer(st, dst, st.RR[gn]) + base;
+        int* __restrict__ pID = apj_peer(st, dst, st.ID[gn]) + base;
+        for (int i = blockIdx.x * RB_BLOCK + threadIdx.x; i < n; i += gridDim.x * RB_BLOCK) {
+            pXY[i] = st.XY[h][s0 + i]; pCS[i] = st.CS[h][s0 + i]; pRR[i] = st.RR[gn][s0 + i]; pID[i] = st.ID[gn][s0 + i];
+        }
+        int* __restrict__ pgs = apj_peer(st, dst, st.gstart) + ((size_t)gn * 2 + side) * (b + 1);
+        for (int r = blockIdx.x * RB_BLOCK + threadIdx.x; r <= b; r += gridDim.x * RB_BLOCK)
+            pgs[r] = (int)base + min(start[c_lo + r] - s0, n);
+        if (blockIdx.x == 0 && threadIdx.x == 0) apj_peer(st, dst, st.mail)->ghost_n[gn][side] = n;
     }
 }
 
@@ -250,8 +370,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
     const int sys = blockIdx.x;
     SysCtl* __restrict__ ctl = st.ctl + sys;
     if (!ctl->stale) return;
-    const int b = ctl->b;
+    const int b = ctl->b, w = ctl->ncols, col0 = ctl->col0;
     const int* __restrict__ start = st.cell_start + ctl->cell_base;
+    const int* __restrict__ gs = st.slab ? st.gstart + (size_t)(ctl->gen ^ 1) * 2 * (b + 1) : nullptr;   // ghost columns [side][b+1]
     int* __restrict__ col_blk = st.col_blk + ctl->col_base;
     const int* __restrict__ box = st.BOX[ctl->gen ^ 1];   // the half reorder just wrote
     __shared__ int s_warp[SCAN_BLOCK / 32];
@@ -261,9 +382,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int ppb = st.ppb;
     // exclusive scan over columns of ceil(n_X / ppb)
-    for (int base = 0; base < b; base += SCAN_BLOCK) {
+    for (int base = 0; base < w; base += SCAN_BLOCK) {
         const int X = base + threadIdx.x;
-        const int nb = (X < b) ? (start[(X + 1) * b] - start[X * b] + ppb - 1) / ppb : 0;
+        const int nb = (X < w) ? (start[(X + 1) * b] - start[X * b] + ppb - 1) / ppb : 0;
         int inc = nb;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -283,17 +404,18 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
         }
         __syncthreads();
         const int carry = s_carry;
-        if (X < b) col_blk[X] = carry + (wid ? s_warp[wid - 1] : 0) + inc - nb;
+        if (X < w) col_blk[X] = carry + (wid ? s_warp[wid - 1] : 0) + inc - nb;
         __syncthreads();
         if (threadIdx.x == SCAN_BLOCK - 1) s_carry = carry + s_warp[SCAN_BLOCK / 32 - 1];
         __syncthreads();
     }
     const int nblk = s_carry;
-    if (threadIdx.x == 0) col_blk[b] = nblk;
+    if (threadIdx.x == 0) col_blk[w] = nblk;
     // descriptors: one thread per column walks that column's blocks
     int tile_max = 0, over = 0;
-    for (int X = threadIdx.x; X < b; X += SCAN_BLOCK) {
+    for (int X = threadIdx.x; X < w; X += SCAN_BLOCK) {
         const int c0 = start[X * b], c1 = start[(X + 1) * b];
+        const int Xg = X + col0;                           // column of the global grid
         int blk = col_blk[X];
         for (int g0 = c0; g0 < c1; g0 += ppb, blk++) {
             TileDesc d;
@@ -302,11 +424,16 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
             const int cy0 = box[g0] - X * b, cy1 = box[g0 + d.n - 1] - X * b;
             int slots = 0, npieces = 0;
             // minimum-image wraps can only fire in blocks that touch the periodic seam
-            int wraps = (b < 7 || X == 0 || X == b - 1 || cy0 == 0 || cy1 == b - 1) ? 1 : 0;
+            int wraps = (b < 7 || Xg == 0 || Xg == b - 1 || cy0 == 0 || cy1 == b - 1) ? 1 : 0;
             for (int dx = -1; dx <= 1; dx++) {
                 int Xd = X + dx;
-                if (Xd < 0) Xd += b; else if (Xd >= b) Xd -= b;
-                const int* __restrict__ cs = start + Xd * b;
+                const int* __restrict__ cs;
+                if (st.slab) {                             // beyond the slab: the neighbour's column, held as a ghost
+                    cs = Xd < 0 ? gs : (Xd >= w ? gs + (b + 1) : start + Xd * b);
+                } else {
+                    if (Xd < 0) Xd += b; else if (Xd >= b) Xd -= b;
+                    cs = start + Xd * b;
+                }
                 const int lo = cy0 - 1, hi = cy1 + 1;
                 const int before = slots;
                 int piece_of_own = -1;
@@ -324,7 +451,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
                 if (dx == 0)     // the block's own particles sit in the first piece of the middle column
                     d.own_slot = 1 + before + (g0 - d.pstart[piece_of_own]);   // slots are 1-based (0 = sentinel)
             }
-            d.info = npieces | (wraps << 8);           // list words are filled in by verlet_build
+            d.info = npieces | (wraps ? APJ_INFO_WRAPS : 0);   // list words are filled in by verlet_build
+            if (st.slab && X == 0) d.info |= APJ_INFO_PUSH_LEFT;
+            if (st.slab && X == w - 1) d.info |= APJ_INFO_PUSH_RIGHT;
             tile_max = max(tile_max, slots);
             if (slots > st.tile_cap || slots > 4094) over = 1;   // 16-bit entries hold slot * 16
             st.tiles[(long long)sys * st.maxblk + blk] = d;
@@ -335,6 +464,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
     __syncthreads();
     if (threadIdx.x == 0) {
         ctl->nblk = nblk;
+        ctl->last_col_start = start[(w - 1) * b];
         ctl->tile_max = s_tile_max;
         if (s_over) ctl->overflow |= 2;
     }
@@ -353,7 +483,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
 constexpr double BUILD_NEAR2 = 3.15 * 3.15;   // rn + half the skin, squared
 
 template <bool WRAP, class F>
-__device__ __forceinline__ void for_each_candidate(const TileDesc& sd, const int* __restrict__ start, const int b, const int cx,
+__device__ __forceinline__ void for_each_candidate(const TileDesc& sd, const int* __restrict__ start, const int* __restrict__ gs,
+                                                   const int w, const int b, const int cx,
                                                    const int cy, const double2* __restrict__ sXY, const int own,
                                                    const double2 me, const double L, const double Lh, const double rs2, F&& f) {
     auto run = [&](int a, int e) {
@@ -370,8 +501,13 @@ __device__ __forceinline__ void for_each_candidate(const TileDesc& sd, const int
     };
     for (int dcx = -1; dcx <= 1; dcx++) {
         int col = cx + dcx;
-        if (col < 0) col += b; else if (col >= b) col -= b;
-        const int* __restrict__ cs = start + col * b;
+        const int* __restrict__ cs;
+        if (gs) {                                      // slab mode: ghost columns beyond the slab
+            cs = col < 0 ? gs : (col >= w ? gs + (b + 1) : start + col * b);
+        } else {
+            if (col < 0) col += b; else if (col >= b) col -= b;
+            cs = start + col * b;
+        }
         if (cy >= 1 && cy <= b - 2) {
             run(cs[cy - 1], cs[cy + 2]);               // rows cy-1..cy+1 are one contiguous run
         } else {
@@ -391,14 +527,15 @@ __device__ __forceinline__ void build_lists(const DevState& st, SysCtl* __restri
     const int g = sd.g0 + t;
     const int gen = ctl->gen ^ 1;                      // the half reorder just wrote
     const int* __restrict__ start = st.cell_start + ctl->cell_base;
-    const int b = ctl->b;
+    const int b = ctl->b, w = ctl->ncols;
+    const int* __restrict__ gs = st.slab ? st.gstart + (size_t)gen * 2 * (b + 1) : nullptr;
     const double L = ctl->L, Lh = ctl->Lover2, rs2 = st.rs2;
     const int own = sd.own_slot + t;
     const double2 me = sXY[own];
     const int c = st.BOX[gen][g];
     const int cx = c / b, cy = c - cx * b;
     int n_near = 0, total = 0;
-    for_each_candidate<WRAP>(sd, start, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int, double d2) {
+    for_each_candidate<WRAP>(sd, start, gs, w, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int, double d2) {
         total++;
         if (d2 < BUILD_NEAR2) n_near++;
     });
@@ -411,7 +548,7 @@ __device__ __forceinline__ void build_lists(const DevState& st, SysCtl* __restri
         out[(((size_t)(kk >> 2) * st.tb + t * G + sub) * 4 + (kk & 3)) * 2 + (e & 1)] = (unsigned short)v;
     };
     int c_near = 0, c_far = n_near;
-    for_each_candidate<WRAP>(sd, start, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int s, double d2) {
+    for_each_candidate<WRAP>(sd, start, gs, w, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int s, double d2) {
         const int e = (d2 < BUILD_NEAR2) ? c_near++ : c_far++;
         if (e < S) put(e, (unsigned)s << 4);
     });
@@ -449,7 +586,7 @@ __global__ void __launch_bounds__(APJ_TB_MAX) apj_verlet_build_kernel(const DevS
     unsigned dep = 0;
     apj_mbar_wait(&s_bar, 0, dep);
     if (threadIdx.x < sd.n) {
-        if ((sd.info >> 8) & 1) build_lists<true>(st, ctl, sd, bg, sXY);
+        if (sd.info & APJ_INFO_WRAPS) build_lists<true>(st, ctl, sd, bg, sXY);
         else build_lists<false>(st, ctl, sd, bg, sXY);
     }
 }
@@ -471,6 +608,8 @@ __global__ void apj_finish_rebuild_kernel(const DevState st) {
     ctl->n_rebuilds += 1;
     ctl->save_old = 0;
     ctl->stale = 0;
+    ctl->n_own = ctl->n_end - ctl->p0;
+    if (st.slab) st.mail->inbox_count = 0;   // neighbours push again only after the next step was exchanged
 }
 
 }  // namespace
@@ -478,9 +617,13 @@ __global__ void apj_finish_rebuild_kernel(const DevState st) {
 void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nbox, int max_b) {
     (void)max_b;
     // fixed grids: ~16 blocks of 128 threads per SM in total, shared out over the systems
-    const int bps = std::max(1, std::min((st.N + RB_BLOCK - 1) / RB_BLOCK, (148 * 16 + st.n_sys - 1) / st.n_sys));
+    const int bps = std::max(1, std::min((st.cap + RB_BLOCK - 1) / RB_BLOCK, (148 * 16 + st.n_sys - 1) / st.n_sys));
     const int grid = st.n_sys * bps;
     apj_bin_count_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
+    if (st.slab) {
+        apj_slab_sync_kernel<<<1, 32, 0, l.stream>>>(st, 1);       // all migrants delivered
+        apj_absorb_kernel<<<std::max(1, std::min((st.mcap + RB_BLOCK - 1) / RB_BLOCK, 148 * 4)), RB_BLOCK, 0, l.stream>>>(st);
+    }
     const int chunks = (max_nbox + SCAN_CHUNK - 1) / SCAN_CHUNK;       // == DevState::scan_chunks
     dim3 gc(chunks, st.n_sys);
     apj_scan_chunk_sums_kernel<<<gc, SCAN_BLOCK, 0, l.stream>>>(st, chunks);
@@ -490,11 +633,16 @@ void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nb
     dim3 gs(std::max(1, std::min((max_nbox + RB_BLOCK - 1) / RB_BLOCK, (148 * 16 + st.n_sys - 1) / st.n_sys)), st.n_sys);
     apj_cell_sort_kernel<<<gs, RB_BLOCK, 0, l.stream>>>(st);
     apj_reorder_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
+    if (st.slab) {
+        apj_push_ghosts_kernel<<<std::max(1, std::min((st.gcap + RB_BLOCK - 1) / RB_BLOCK, 148 * 4)), RB_BLOCK, 0, l.stream>>>(st);
+        apj_slab_sync_kernel<<<1, 32, 0, l.stream>>>(st, 2);       // ghost columns in place on every rank
+    }
     apj_make_tiles_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st);
     apj_verlet_build_kernel<<<st.n_sys * st.maxblk, st.ppb, (size_t)(st.tile_cap + 1) * 16, l.stream>>>(st);
     apj_finish_rebuild_kernel<<<(st.n_sys + 63) / 64, 64, 0, l.stream>>>(st);
-    if (l.launch_counter) (*l.launch_counter) += 10;
+    if (l.launch_counter) (*l.launch_counter) += apj_rebuild_chain_launches(st);
 }
+int apj_rebuild_chain_launches(const DevState& st) { return st.slab ? 14 : 10; }
 
 int apj_max_list_capacity() { return MAX_S; }
 int apj_scan_chunk_cells() { return SCAN_CHUNK; }

@@ -113,7 +113,7 @@ __device__ __forceinline__ void sweep(PairAcc& acc, const int nw, const uint4 (&
 #ifndef APJ_BLOCKS_256
 #define APJ_BLOCKS_256 4
 #endif
-template <int TB, int G, bool INJECT>
+template <int TB, int G, bool INJECT, bool SLAB>
 __global__ void __launch_bounds__(TB, (TB == 256 ? APJ_BLOCKS_256 : 8))
 apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const int always_full) {
     constexpr int PPB = TB / G;                        // particles per block
@@ -149,7 +149,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     __syncthreads();
 
     const int npieces = sd.info & 0xff;
-    const bool wraps = (sd.info >> 8) & 1;
+    const bool wraps = (sd.info & APJ_INFO_WRAPS) != 0;
 
     if (t == 0) {   // stage the tile: <= 6 pieces x 3 arrays, one TMA bulk copy each
         int slots = 0;
@@ -265,6 +265,19 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         st.XY[cur ^ 1][g] = make_double2(x, y);
         st.CS[cur ^ 1][g] = make_double2(cs, sn);
         st.XR[cur ^ 1][g] = make_double2(xrn, yrn);
+        if (SLAB) {   // halo exchange fused into the epilogue: boundary columns are stored straight into the
+                      // neighbours' ghost slots (peer memory over NVLink), in the half they read next step
+            if (sd.info & APJ_INFO_PUSH_LEFT) {    // column 0 starts at slot 0 -> left neighbour's RIGHT ghost column
+                const long long pg = (long long)st.cap + st.gcap + g;
+                apj_peer(st, st.left, st.XY[cur ^ 1])[pg] = make_double2(x, y);
+                apj_peer(st, st.left, st.CS[cur ^ 1])[pg] = make_double2(cs, sn);
+            }
+            if (sd.info & APJ_INFO_PUSH_RIGHT) {   // last owned column -> right neighbour's LEFT ghost column
+                const long long pg = (long long)st.cap + (g - ctl->last_col_start);
+                apj_peer(st, st.right, st.XY[cur ^ 1])[pg] = make_double2(x, y);
+                apj_peer(st, st.right, st.CS[cur ^ 1])[pg] = make_double2(cs, sn);
+            }
+        }
         if (always_full || step + 1 == ctl->target) {   // fields only observables read
             st.V[gen][g] = make_double2(vx, vy);
             st.PHI[gen][g] = phi;
@@ -299,9 +312,10 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     unsigned* __restrict__ gticket = st.gticket + (long long)sys * st.maxgrp;
     double4* __restrict__ gpart = st.gpartials + (long long)sys * st.maxgrp;
     unsigned last = 0;
+    if (SLAB) __syncwarp();   // peer stores of the other lanes are ordered before lane 0's system-scope fence
     if (lane == 0) {
         st.partials[bg] = make_double4(sum_x, sum_y, top1, top2);
-        __threadfence();
+        if (SLAB) __threadfence_system(); else __threadfence();
         last = (atomicAdd(gticket + grp, 1u) == (unsigned)gsize - 1u) ? 1u : 0u;
     }
     last = __shfl_sync(0xffffffffu, last, 0);
@@ -325,7 +339,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     if (lane == 0) {
         gticket[grp] = 0u;
         gpart[grp] = a;
-        __threadfence();
+        if (SLAB) __threadfence_system(); else __threadfence();
         last = (atomicAdd(&ctl->ticket, 1u) == (unsigned)ngrp - 1u) ? 1u : 0u;
     }
     last = __shfl_sync(0xffffffffu, last, 0);
@@ -358,6 +372,19 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         const double b1 = __shfl_xor_sync(0xffffffffu, a.z, o), b2 = __shfl_xor_sync(0xffffffffu, a.w, o);
         apj_top2_merge(a.z, a.w, b1, b2);
     }
+    if (SLAB) {
+        // this rank's partial goes to every rank of the box (own mailbox included); the commit kernel
+        // that follows folds them in rank order, so all ranks take the same decision
+        if (lane == 0) ctl->ticket = 0u;
+        const unsigned long long ep = ctl->seq[0];
+        if (lane < st.nranks) {
+            SlabMail* m = apj_peer(st, lane, st.mail);
+            m->part[ep & 1][st.rank] = a;
+            __threadfence_system();
+            apj_st_release_sys(&m->flag[0][st.rank], ep + 1);
+        }
+        return;
+    }
     if (lane == 0) {
         ctl->ticket = 0u;
         if (sqrt(a.z) + sqrt(a.w) > st.skin) {   // jamming.cpp:611
@@ -374,6 +401,44 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     }
 }
 
+// Slab mode: second half of the step. Waits for the partials of all ranks (pushed by their step
+// kernels, see above), folds them in rank order and takes the reference's decision
+// (jamming.cpp:611): commit the speculative step or drop it and rebuild. One warp.
+__global__ void apj_slab_commit_kernel(const DevState st) {
+    SysCtl* __restrict__ ctl = st.ctl;
+    if (ctl->stale || ctl->step >= ctl->target) return;   // the step kernel exited on the same test: nothing was sent
+    const int lane = threadIdx.x;
+    const unsigned long long ep = ctl->seq[0];
+    bool ok = true;
+    if (lane < st.nranks && !ctl->slab_err) ok = apj_wait_flag(&st.mail->flag[0][lane], ep + 1, st.timeout_ns);
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane != 0) return;
+    ctl->seq[0] = ep + 1;
+    if (!ok || ctl->slab_err) {   // a peer never showed up: stop stepping, the host reports it
+        ctl->slab_err |= 1;
+        ctl->target = ctl->step;
+        return;
+    }
+    double4 a = make_double4(0.0, 0.0, 0.0, 0.0);
+    for (int r = 0; r < st.nranks; r++) {
+        const double2* q = reinterpret_cast<const double2*>(&st.mail->part[ep & 1][r]);
+        const double2 b01 = __ldcg(q), b23 = __ldcg(q + 1);
+        a.x += b01.x; a.y += b01.y;
+        apj_top2_merge(a.z, a.w, b23.x, b23.y);
+    }
+    if (sqrt(a.z) + sqrt(a.w) > st.skin) {   // jamming.cpp:611
+        ctl->stale = 1;
+        ctl->save_old = 1;
+        ctl->n_discarded += 1;
+    } else {
+        ctl->COM[0] = a.x / st.N;            // calculate_COM (jamming.cpp:761-774), N of the global box
+        ctl->COM[1] = a.y / st.N;
+        ctl->cur ^= 1;
+        ctl->step += 1;
+        ctl->no_self_once = 0;
+    }
+}
+
 size_t step_smem_bytes(const DevState& st) {
     return (size_t)(st.tile_cap + 1) * 48 + (st.G > 1 ? (size_t)st.ppb * 32 : 0);
 }
@@ -381,8 +446,10 @@ size_t step_smem_bytes(const DevState& st) {
 template <int TB, int G>
 int configure(const DevState& st) {
     const int bytes = (int)step_smem_bytes(st);
-    if (cudaFuncSetAttribute(apj_step_kernel<TB, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(apj_step_kernel<TB, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(apj_step_kernel<TB, G, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(apj_step_kernel<TB, G, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(apj_step_kernel<TB, G, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(apj_step_kernel<TB, G, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
     return 0;
 }
 
@@ -390,8 +457,14 @@ template <int TB, int G>
 void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int always_full) {
     const int grid = st.n_sys * st.maxblk;
     const size_t smem = step_smem_bytes(st);
-    if (noise_by_id) apj_step_kernel<TB, G, true><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
-    else apj_step_kernel<TB, G, false><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+    if (st.slab) {
+        if (noise_by_id) apj_step_kernel<TB, G, true, true><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
+        else apj_step_kernel<TB, G, false, true><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+        apj_slab_commit_kernel<<<1, 32, 0, s>>>(st);
+    } else {
+        if (noise_by_id) apj_step_kernel<TB, G, true, false><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
+        else apj_step_kernel<TB, G, false, false><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+    }
 }
 
 }  // namespace
@@ -416,5 +489,5 @@ void apj_launch_step(const DevState& st, const ApjLaunch& l, const double* noise
 #define APJ_LAUNCH(TB, G) launch<TB, G>(st, l.stream, noise_by_id, always_full)
     APJ_DISPATCH(APJ_LAUNCH)
 #undef APJ_LAUNCH
-    if (l.launch_counter) (*l.launch_counter)++;
+    if (l.launch_counter) (*l.launch_counter) += st.slab ? 2 : 1;
 }

@@ -45,7 +45,10 @@ EXPORTS = ["apj_version", "apj_last_error", "apj_create", "apj_destroy", "apj_se
            "apj_skip_self_term_once", "apj_step", "apj_step_injected", "apj_force_rebuild", "apj_sync",
            "apj_get_counters", "apj_get_tuning", "apj_set_reset_counter", "apj_get_geometry", "apj_get_pair_list", "apj_get_cell_lists", "apj_list_stats",
            "apj_order_orientation", "apj_msd", "apj_fluct_area", "apj_spatial_correlations", "apj_vel_hist",
-           "apj_occupancy_hist", "apj_timer_begin", "apj_timer_end", "apj_time_step_kernel"]
+           "apj_occupancy_hist", "apj_timer_begin", "apj_timer_end", "apj_time_step_kernel",
+           # slab mode (bound in slab.py)
+           "apj_slab_create", "apj_slab_info", "apj_slab_export", "apj_slab_connect", "apj_slab_set_timeout", "apj_slab_ready",
+           "apj_slab_upload", "apj_slab_download", "apj_slab_get_pairs"]
 
 _lib = None
 

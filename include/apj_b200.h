@@ -157,6 +157,48 @@ int apj_timer_end(apj_engine* e, float* milliseconds);
  * each step-kernel launch and returns the mean duration (ms) of those that committed. */
 int apj_time_step_kernel(apj_engine* e, int64_t n, float* mean_ms, int64_t* committed);
 
+/* ---- slab mode: ONE periodic box over the GPUs of a node (BASELINE config 4) --------
+ * The global b x b cell grid (Engine::topology, jamming.cpp:356-480) is cut along x into slabs of
+ * whole cell columns, rank r owning columns [r*b/nranks, (r+1)*b/nranks). Each rank runs one handle
+ * on its GPU (one process per GPU, or several handles in one process). All exchange happens on the
+ * device over peer memory (NVLink): the step kernel stores the new {x,y},{cos,sin} of its boundary
+ * columns straight into the neighbours' ghost slots and every rank's {sum x_real, top-2 displacement}
+ * partial into every rank's mailbox; a one-warp commit kernel folds the partials in rank order, so all
+ * ranks take the reference's rebuild decision (newSkinList, jamming.cpp:587-617) on the same step; at a
+ * rebuild, particles that left the slab are handed to the owning neighbour with peer atomics and the
+ * ghost columns are re-sent. Results do not depend on the decomposition (Philox counters and list
+ * order are keyed by particle id / global cell), except for the rounding of COM.
+ * Calls marked [collective] must be made by all ranks (one host thread per rank) together. */
+/* cfg->n is the particle count of the GLOBAL box, cfg->n_systems must be 1; capacity = particle slots of
+ * this rank (0 -> n/nranks * 1.25 + four columns). */
+int apj_slab_create(const apj_config* cfg, double L, int32_t rank, int32_t nranks, int64_t capacity, apj_engine** out);
+/* out[8] = {rank, nranks, first owned column, owned columns, capacity, ghost-column capacity, owned particles, arena bytes} */
+int apj_slab_info(apj_engine* e, int64_t* out8);
+/* The peer-visible arena of this rank: a 64-byte cudaIpcMemHandle_t for ranks in other processes and
+ * the local device pointer for handles in the same process. Either output may be NULL. */
+int apj_slab_export(apj_engine* e, void* handle64, uint64_t* local_ptr);
+/* Make rank `peer`'s arena addressable: same_process_ptr != 0 -> use that pointer (peer_device = its CUDA
+ * device, for cudaDeviceEnablePeerAccess); otherwise open the IPC handle. */
+int apj_slab_connect(apj_engine* e, int32_t peer, const void* handle64, uint64_t same_process_ptr, int32_t peer_device);
+/* Device-side waits for a peer give up after this many seconds (default 20) and the call returns
+ * APJ_E_STATE instead of hanging. */
+int apj_slab_set_timeout(apj_engine* e, double seconds);
+/* After every peer is connected: builds the step graph. */
+int apj_slab_ready(apj_engine* e);
+/* [collective] n_local particles (any subset; ids[k] = original particle index in [0, N)) in caller order.
+ * Particles not in this rank's columns are migrated to the neighbour (adjacent slabs only). COM is NOT
+ * derived: set it on every rank with apj_set_com (global mean of x_real). */
+int apj_slab_upload(apj_engine* e, const apj_state* host, const int32_t* ids, int64_t n_local);
+/* Owned particles in device (cell) order with their ids; *n_local receives the count (query with ids == NULL). */
+int apj_slab_download(apj_engine* e, apj_state* host, int32_t* ids, int64_t cap, int64_t* n_local);
+/* Pairs (id_i, id_j), id_j > id_i, of the owned particles' Verlet lists including ghost partners: the
+ * union over ranks is the reference's half-list pair set (each pair exactly once). pairs[2*cap]. */
+int apj_slab_get_pairs(apj_engine* e, int32_t* pairs, int64_t cap_pairs, int64_t* total);
+/* On a slab handle apj_step, apj_step_injected (noise indexed by global id), apj_force_rebuild and
+ * apj_mark_origin are [collective]; apj_order_orientation (orient only), apj_msd, apj_fluct_area,
+ * apj_vel_hist, apj_occupancy_hist and the COM left by apj_mark_origin are this rank's ADDITIVE share
+ * (already divided by the global N where the reference divides): sum them over ranks. */
+
 #ifdef __cplusplus
 }
 #endif

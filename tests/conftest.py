@@ -6,6 +6,9 @@ import sys
 
 import pytest
 
+# several slab ranks share the one GPU of the test box: give every handle's stream its own hardware queue
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -1,0 +1,138 @@
+"""Slab decomposition of ONE periodic box (BASELINE config 4) against (i) the periodic
+single-handle engine -- positions must be BIT-IDENTICAL, because Philox counters are keyed by particle
+id and list order by global cell, so the decomposition can only change the rounding of COM -- and
+(ii) the oracle (pair set bit-exact, injected single step <= 1e-12). Several ranks share the one GPU of
+the test box (one host thread per rank, peers are plain device pointers); the exchange code is the
+same peer-store / peer-atomic / flag path that runs over NVLink between GPUs."""
+import numpy as np
+import pytest
+
+from _util import DEV2ORC, device_from_state, random_system, rel_err, wrapped_abs_diff
+from oracle.pyoracle import PI, OracleSim
+from test_gpu_parity import relaxed_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def slab_from_state(s, nranks, seed=12345, **kw):
+    from active_particle_jamming_b200.slab import SlabBox
+    box = SlabBox(len(s["x"]), s["L"], nranks, seed=seed, **kw)
+    box.set_activity(s["CFself"], s["CTnoise"])
+    box.upload(**{d: s[o] for d, o in DEV2ORC.items()})
+    box.set_com(com=[s["COMx"], s["COMy"]], com0=[s["COM0x"], s["COM0y"]], com_old=[s["COMoldx"], s["COMoldy"]])
+    box.set_reset_counter(int(s["resetCounter"]))
+    return box
+
+
+@pytest.mark.parametrize("nranks,lanes", [(1, 4), (2, 4), (3, 1), (4, 2)])
+def test_slab_pairs_and_single_step_match_oracle(nranks, lanes):
+    """Gates 1 and 2 of north_star on the decomposed box."""
+    N, rho = 4096, 0.9
+    o, rng = relaxed_oracle(N, rho, seed=300 + nranks, l_s=0.5, l_n=0.3)
+    L = o.scalars()["L"]
+    box = slab_from_state(o.state(), nranks, lanes_per_particle=lanes)
+    try:
+        assert sum(box.n_own()) == N
+        o.assign(); o.build()
+        assert np.array_equal(box.pair_set(), o.pair_set())
+        for k in range(3):
+            # the first step starts from identical state: 1e-12 (gate 2). The next two run on without
+            # re-synchronising; last-bit differences grow ~1 decade per 25 steps (DESIGN.md "Parity")
+            tol = TOL if k == 0 else 1e-10
+            nz = rng.uniform(-PI, PI, N)
+            o.step(nz)
+            box.step_injected(nz)
+            d = box.download()
+            assert np.max(wrapped_abs_diff(d["x"], o.x, L)) <= tol * L and np.max(wrapped_abs_diff(d["y"], o.y, L)) <= tol * L
+            assert rel_err(d["cosp"], o.cosp) <= tol and rel_err(d["sinp"], o.sinp) <= tol
+            assert rel_err(d["vx"], o.vx, floor=1e-2) <= tol and rel_err(d["x_real"], o.xr, floor=L) <= tol
+            sc, c = o.scalars(), box.get_com()
+            assert abs(c["COM"][0] - sc["COMx"]) <= tol * L and abs(c["COM"][1] - sc["COMy"]) <= tol * L
+            assert box.counters()["resetCounter"] == sc["resetCounter"]
+    finally:
+        box.close()
+        o.close()
+
+
+@pytest.mark.parametrize("nranks,lanes,N", [(1, 4, 4096), (2, 4, 4096), (3, 2, 6000), (4, 1, 20000), (8, 1, 40000)])
+def test_slab_free_running_bit_identical_to_periodic(nranks, lanes, N):
+    """300 Philox steps with frequent rebuilds and migration across slab edges (lambda_s = 0.5): every
+    rank count gives the bits of the single-GPU periodic engine."""
+    rho, seed = 0.9, 77
+    o, _ = relaxed_oracle(N, rho, seed=seed + nranks, l_s=0.5, l_n=0.3, presteps=40)
+    s = o.state()
+    L = s["L"]
+    o.close()
+    # 40 relaxation steps leave a few dense clusters of the random start: lists of up to ~50 entries
+    e = device_from_state(s, seed=seed, lanes_per_particle=lanes, max_neighbors=64)
+    box = slab_from_state(s, nranks, seed=seed, lanes_per_particle=lanes, max_neighbors=64)
+    try:
+        own0 = box.n_own()
+        moved = 0
+        for chunk in (1, 50, 120, 129):
+            e.step(chunk); box.step(chunk)
+            ce, cb = e.counters(), box.counters()
+            assert cb["step"] == ce["step"] and cb["resetCounter"] == ce["resetCounter"]
+            own = box.n_own()
+            assert sum(own) == N
+            moved += int(own != own0)
+            own0 = own
+            a, b = e.download(), box.download()
+            for f in ("x", "y", "cosp", "sinp", "x_real", "y_real", "x_old", "y_old", "x0", "y0", "R"):
+                assert np.array_equal(a[f], b[f]), "%s differs after %d steps" % (f, ce["step"])
+            assert np.array_equal(a["box"], b["box"])
+            assert np.array_equal(e.pair_set(), box.pair_set())
+        assert ce["resetCounter"] >= 3, "the run was meant to cross several rebuilds"
+        if nranks > 1:
+            assert moved > 0, "no particle ever changed rank: migration untested"
+        # observables: additive shares of the ranks against the periodic engine
+        assert abs(box.order_orientation()[0][0] - e.order_orientation()[0][0]) <= TOL
+        assert abs(box.msd()[0] - e.msd()[0]) <= TOL * max(1.0, e.msd()[0])
+        assert np.array_equal(box.occupancy_hist(), e.occupancy_hist())
+        assert abs(box.list_stats()[0] - e.list_stats()[0]) <= 1e-12
+    finally:
+        e.close()
+        box.close()
+
+
+def test_slab_mark_origin_and_relax_ramp():
+    """start() :191-203 and the relax() ramp on a decomposed box."""
+    N, rho, seed = 8192, 0.9, 5
+    R, L, x, y, phi = random_system(N, rho, seed)
+    from active_particle_jamming_b200 import DeviceEngine
+    from active_particle_jamming_b200.slab import SlabBox
+    e = DeviceEngine(N, L, seed=seed, lanes_per_particle=2)
+    box = SlabBox(N, L, 3, seed=seed, lanes_per_particle=2)
+    try:
+        for q in (e, box):
+            q.set_activity(0.0, 0.5)
+            q.upload(x=x, y=y, R=R, phi=phi)
+            q.step(60)
+            q.set_activity(0.3, 0.5)
+            q.set_ramp(50)
+            q.step(80)
+            q.mark_origin()
+            q.step(40)
+        a, b = e.download(), box.download()
+        for f in ("x", "y", "cosp", "x0", "y0", "x_real"):
+            assert np.array_equal(a[f], b[f]), f
+        assert abs(box.msd()[0] - e.msd()[0]) <= TOL * max(1.0, e.msd()[0])
+        ca, cb = e.get_com(), box.get_com()
+        assert np.max(np.abs(ca["COM0"] - cb["COM0"])) <= TOL * L
+    finally:
+        e.close()
+        box.close()
+
+
+def test_slab_capacity_overflow_is_loud():
+    from active_particle_jamming_b200 import ApjError
+    from active_particle_jamming_b200.slab import SlabBox
+    N, rho = 4096, 0.9
+    R, L, x, y, phi = random_system(N, rho, 3)
+    box = SlabBox(N, L, 2, capacity=N // 2 - 200)
+    try:
+        with pytest.raises(ApjError):
+            box.upload(x=x, y=y, R=R, phi=phi)
+    finally:
+        box.close()
