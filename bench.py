@@ -196,24 +196,42 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---- this rank's share. n_gpus > 1: the box is cut into n_gpus parts of n_tot / n_gpus particles.
-    n_loc = n_tot // world
-    parallelism = "single" if world == 1 else "replicas%d" % world
-    R, L, x, y, phi = synthetic_state(n_loc, rho, 12345 + rank)
-    Ls = [L] * reps
-    if reps > 1:
-        parts = [synthetic_state(n_loc, rho, 12345 + rank * reps + s) for s in range(reps)]
-        Ls = [p[1] for p in parts]
-        R, x, y, phi = (np.concatenate([p[k] for p in parts]) for k in (0, 2, 3, 4))
-
     def pinned(arr):
-        t = torch.empty(arr.shape, dtype=torch.float64, pin_memory=True)
+        t = torch.empty(arr.shape, dtype=torch.float64 if arr.dtype == np.float64 else torch.int32, pin_memory=True)
         t.numpy()[...] = arr
         return t.numpy()
-    host = {k: pinned(v) for k, v in dict(x=x, y=y, R=R, phi=phi).items()}
 
-    e = DeviceEngine(n_loc, Ls, n_systems=reps, device=local, seed=12345 + rank, max_neighbors=64)
-    e.upload(**host)
+    # ---- this rank's share.
+    #  * one box (reps == 1), n_gpus > 1: the SAME periodic box of n_tot particles, cut along x into slabs of
+    #    whole cell columns, one slab per GPU; halo / partial / migration exchange on the device over NVLink
+    #    peer memory (include/apj_b200.h "slab mode"). Total work is fixed: strong scaling.
+    #  * replica workloads (reps > 1): independent ensembles per GPU, no communication: weak scaling.
+    slab = world > 1 and reps == 1
+    if slab:
+        from active_particle_jamming_b200.slab import DistSlab
+        R, L, x, y, phi = synthetic_state(n_tot, rho, 12345)               # every rank draws the same box, keeps its slab
+        e = DistSlab(n_tot, L, device=local, seed=12345, max_neighbors=64)
+        me = e.local[0]
+        e.upload(x=x, y=y, R=R, phi=phi)
+        del R, x, y, phi
+        n_loc = me.info()["n_own"]
+        parallelism = "slab%d (periodic slabs of whole cell columns along x; device-side peer-memory halo push fused into the " \
+                      "step kernel, all-rank partial exchange + commit, peer-atomic migration at rebuild)" % world
+        scaling = "strong"
+    else:
+        n_loc = n_tot
+        parallelism = "single" if world == 1 else "replicas: %d independent ensembles per GPU, no communication" % reps
+        scaling = "strong" if world == 1 else "weak"
+        R, L, x, y, phi = synthetic_state(n_loc, rho, 12345 + rank)
+        Ls = [L] * reps
+        if reps > 1:
+            parts = [synthetic_state(n_loc, rho, 12345 + rank * reps + s) for s in range(reps)]
+            Ls = [p[1] for p in parts]
+            R, x, y, phi = (np.concatenate([p[k] for p in parts]) for k in (0, 2, 3, 4))
+        host = {k: pinned(v) for k, v in dict(x=x, y=y, R=R, phi=phi).items()}
+        e = DeviceEngine(n_loc, Ls, n_systems=reps, device=local, seed=12345 + rank, max_neighbors=64)
+        me = e
+        e.upload(**host)
     e.skip_self_term_once()
     trelax, ttherm = (50, 50) if a.no_relax else RELAX                     # relax(): jamming.cpp:482-525
     e.set_activity(0.0, l_n); e.step(trelax)
@@ -222,24 +240,26 @@ def main():
 
     # ---- device-resident throughput
     e.step(W)
-    c0 = e.counters()
+    c0 = me.counters()
     smi = ClockSampler(local)
     barrier()
     t0w = time.time()
-    e.timer_begin()
+    me.timer_begin()
     e.step(K)
-    ms = e.timer_end()
+    ms = me.timer_end()
     barrier()
     t1w = time.time()
-    c1 = e.counters()
+    c1 = me.counters()
     ms = max_over_ranks(ms)
     clocks = smi.window(t0w, t1w)
-    particles = sum_over_ranks(float(n_loc * reps))
+    n_loc = me.info()["n_own"] if slab else n_loc
+    particles = float(n_tot) if slab else sum_over_ranks(float(n_loc * reps))
     value = particles * K / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (fused step kernel): event pair around every launch
-    n_full, list_max = e.list_stats(0)
-    kms, committed = e.time_step_kernel(min(max(K, 16), 512))
+    n_full, list_max = e.list_stats() if slab else e.list_stats(0)
+    barrier()
+    kms, committed = me.time_step_kernel(min(max(K, 16), 512))
     b_alg = 128.0 + 4.0 * n_full                                           # bytes per particle-step
     peaks = {}
     try:
@@ -257,37 +277,48 @@ def main():
         pass
 
     # ---- end to end: a whole job through the host-facing API, host buffers in, host buffers out
-    st_host = e.download()
-    up = {k: pinned(st_host[k]) for k in ("x", "y", "x_real", "y_real", "x0", "y0", "x_old", "y_old", "R", "phi", "cosp", "sinp", "vx", "vy")}
-    box_host = st_host["box"]
-    com = [e.get_com(s) for s in range(reps)]
+    F14 = ("x", "y", "x_real", "y_real", "x0", "y0", "x_old", "y_old", "R", "phi", "cosp", "sinp", "vx", "vy")
+    if slab:
+        ids_host, st_host = me.download_local(F14)
+        ids_host = pinned(ids_host)
+        com = [me.get_com(0)]
+    else:
+        st_host = e.download()
+        box_host = st_host["box"]
+        com = [e.get_com(s) for s in range(reps)]
+    up = {k: pinned(st_host[k]) for k in F14}
     barrier()
     tj0 = time.perf_counter()
-    e.upload(box=box_host, **up)                                           # H2D: 14 fp64 + 1 int32 per particle
-    for s in range(reps):
-        e.set_com(s, com=com[s]["COM"], com0=com[s]["COM0"], com_old=com[s]["COM_old"])
+    if slab:
+        e._each(lambda r: r.upload_local(ids_host, **up))                  # H2D: 14 fp64 + 1 int32 (id) per owned particle
+        e.set_com(com=com[0]["COM"], com0=com[0]["COM0"], com_old=com[0]["COM_old"])
+    else:
+        e.upload(box=box_host, **up)                                       # H2D: 14 fp64 + 1 int32 per particle
+        for s in range(reps):
+            e.set_com(s, com=com[s]["COM"], com0=com[s]["COM0"], com_old=com[s]["COM_old"])
     done = 0
     while done < K:                                                        # driver cadence: order/orientation/COM/MSD every 100 steps (:218-239)
         n = min(100, K - done)
         e.step(n); done += n
-        e.order_orientation(); e.msd(); e.get_com(0)
-    out = e.download()                                                     # D2H: full state
+        e.order_orientation(); e.msd(); me.get_com(0)
+    out = me.download_local(F14)[1] if slab else e.download()              # D2H: full state
     barrier()
     tj1 = time.perf_counter()
     tj = max_over_ranks(tj1 - tj0)
-    nb = n_loc * reps
+    nb = particles if slab else sum_over_ranks(float(n_loc * reps))
     e2e = {"value": particles * K / tj, "unit": "particle-steps/s", "h2d_bytes_per_step": (14 * 8 + 4) * nb / K,
-           "d2h_bytes_per_step": ((14 * 8 + 4) * nb + 40 * ((K + 99) // 100) * reps) / K, "job_seconds": tj,
-           "what": "apj_upload_state (pinned host SoA) + K x apj_step with order/orientation/MSD/COM read back every 100 steps + apj_download_state"}
+           "d2h_bytes_per_step": ((14 * 8 + 4) * nb + 40 * ((K + 99) // 100) * reps * world) / K, "job_seconds": tj,
+           "what": ("apj_slab_upload" if slab else "apj_upload_state") + " (pinned host SoA) + K x apj_step with order/orientation/MSD/COM "
+                   "read back every 100 steps + " + ("apj_slab_download" if slab else "apj_download_state") + "; bytes are totals over all GPUs"}
     assert np.all(np.isfinite(out["x"]))
 
     line = {"metric": "particle-steps/sec (fp64)", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": a.workload, "what": what, "particles": int(particles), "particles_per_gpu": n_loc * reps, "phi": rho,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": a.workload, "what": what, "particles": int(particles), "particles_per_gpu": int(particles / world), "phi": rho,
                        "lambda_s": l_s, "lambda_n": l_n, "dt": 0.1, "parallelism": parallelism, "relax": [trelax, ttherm],
                        "l2": "state + lists per GPU = %.0f MB, larger than the 126 MB L2: no flush between steps" % (n_loc * reps * (108 + 4 * n_full) / 1e6)
                        if n_loc * reps * 150 > 200e6 else "state fits L2 (%.0f MB): L2-resident by nature of the workload, no flush" % (n_loc * reps * 150 / 1e6),
-                       "rebuilds_in_timed_region": c1["rebuilds"] - c0["rebuilds"], "list_max": list_max, "tuning": e.tuning()},
+                       "rebuilds_in_timed_region": c1["rebuilds"] - c0["rebuilds"], "list_max": list_max, "tuning": me.tuning()},
             "roofline": roofline, "e2e": e2e, "gpu_launches": c1["launches"] - c0["launches"], "clocks": clocks}
     smi.stop()
     if rank == 0 and world == 1 and not a.no_cpu:

@@ -136,3 +136,20 @@ def test_slab_capacity_overflow_is_loud():
             box.upload(x=x, y=y, R=R, phi=phi)
     finally:
         box.close()
+
+
+def test_slab_across_gpus_matches_periodic():
+    """Two or more real GPUs (one process per GPU, cudaIpc peer mappings over NVLink): skipped on a
+    single-GPU box, where the same code paths run with several ranks on one device (tests above)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 8)),
+                        "--master-addr", "127.0.0.1", "--master-port", "29641", os.path.join(root, "scripts", "slab_dist_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
