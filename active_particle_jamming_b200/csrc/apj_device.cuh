@@ -30,6 +30,17 @@
 #define APJ_TB_MAX 256      // largest thread block of the step kernel (particles per block = tb / G)
 #define APJ_MAX_PIECES 6
 #define APJ_MAX_RANKS 8     // slab mode: GPUs of one box
+// Skin-aware sweep length. A list entry whose distance AT BUILD TIME was d_b can only come within
+// rn once the two particles have moved d_b - rn relative to each other, and the relative
+// displacement of any pair since the build is bounded by the sum of the two largest COM-corrected
+// displacements -- the very quantity D = sqrt(l1)+sqrt(l2) the reference's skin test evaluates every
+// step (jamming.cpp:596-611). Lists are stored in APJ_CLASSES distance classes (class k: d_b < rn +
+// (k+1)*skin/APJ_CLASSES), so a step only has to sweep the classes with (k+1)*skin/APJ_CLASSES >= D.
+// The class is chosen from the previous step's D plus a margin and VERIFIED against the step's own D
+// at commit time; a launch that swept too few entries is dropped and re-run (same mechanism as the
+// speculative rebuild), so the result never differs from sweeping the full list.
+#define APJ_CLASSES 4
+#define APJ_CLASS_EPS 1e-9
 // TileDesc::info bits
 #define APJ_INFO_WRAPS (1 << 8)
 #define APJ_INFO_PUSH_LEFT (1 << 9)    // slab mode: the block's particles are the left neighbour's right ghost column
@@ -73,7 +84,14 @@ struct __align__(128) SysCtl {
     int col0, ncols; // slab mode: owned cell columns [col0, col0 + ncols) of the global b x b grid (periodic: 0, b)
     int last_col_start;  // first particle of the last owned column (index of the right neighbour's ghost copy)
     int slab_err;    // sticky: 1 peer wait timed out, 2 migrant crossed more than one slab, 4 capacity exceeded
-    int pad0;
+    // Skin-aware sweep length (see APJ_CLASSES below). skinD = sqrt(l1)+sqrt(l2) of newSkinList
+    // (jamming.cpp:611) for the state the last committed step started from (0 right after a
+    // skin-triggered rebuild); skinDD = its last per-step increase.
+    int trunc_ok;    // 1: x_old is the state the lists were built from (last rebuild was fired by the skin test)
+    int kmin;        // lowest distance class the next launch must sweep (set when a launch swept too few; 0 after a commit)
+    int slab_diag;   // first timed-out wait: (channel + 1) << 16 | mask of the ranks that had not arrived
+    double skinD, skinDD;
+    long long n_retried;   // launches dropped because the sweep length chosen from the previous step's skinD was too short
     unsigned long long seq[3];   // slab mode sequence numbers: step epochs, rebuild phase A, rebuild phase B
 };
 
@@ -109,6 +127,8 @@ struct DevState {
     int max_quads;         // ceil(max_rounds / 4): uint4 rows of the per-block list array
     int tile_cap;          // shared-memory tile capacity in slots (<= 4094; slot 0 is the sentinel)
     double dt, rn2, rs2, skin;  // skin = rs - rn (jamming.cpp:611)
+    double cls2[APJ_CLASSES];   // (rn + (k+1)*skin/APJ_CLASSES)^2: upper bound of build distance^2 of class k (cls2[last] = rs2)
+    int truncate;               // 0 disables the skin-aware sweep length (always the full list)
     unsigned long long seed;
     SysCtl* ctl;
     double2* XY[2];
@@ -123,7 +143,8 @@ struct DevState {
     int* BOX[2];  // internal cell index cy + cx*b (columns contiguous)
     TileDesc* tiles;      // n_sys * maxblk
     unsigned* list32;     // n_sys * maxblk * max_quads * tb uint4
-    int* cnt;             // per particle
+    int* cnt;             // per particle: list length
+    unsigned* cntk;       // per particle: cumulative list length through class k in byte k (byte APJ_CLASSES-1 == cnt)
     int* boxnew;
     int* perm;
     int* cell_count;   // zero between rebuilds
@@ -211,6 +232,22 @@ __device__ __forceinline__ unsigned apj_philox_word0(unsigned c0, unsigned c1, u
 // u / 2^32 * (PI - (-PI)) + (-PI)   
 __device__ __forceinline__ double apj_u32_to_randuni(unsigned u) {
     return __dadd_rn(__dmul_rn(__dmul_rn((double)u, 1.0 / 4294967296.0), APJ_PI - (-APJ_PI)), -APJ_PI);
+}
+
+// lowest distance class that is safe to stop after when the skin-test value is D (APJ_CLASSES-1 = full list)
+__device__ __forceinline__ int apj_class_for(double D, double skin) {
+    int k = 0;
+#pragma unroll
+    for (int c = 0; c < APJ_CLASSES - 1; c++)
+        if (D > (c + 1) * skin / APJ_CLASSES - APJ_CLASS_EPS) k = c + 1;
+    return k;
+}
+// class the launch sweeps: from the previous step's D plus a margin for this step's motion (uniform
+// over the blocks of a system: reads only fields no block writes before the commit)
+__device__ __forceinline__ int apj_sweep_class(const SysCtl* ctl, const DevState& st) {
+    if (!st.truncate || !ctl->trunc_ok) return APJ_CLASSES - 1;
+    const int k = apj_class_for(ctl->skinD + 2.0 * ctl->skinDD + 0.01, st.skin);
+    return k > ctl->kmin ? k : ctl->kmin;
 }
 
 // top-2 merge of two (largest, second) pairs -- the multiset the reference's sequential scan

@@ -30,6 +30,7 @@ struct apj_engine {
     long long launches = 0;
     bool have_state = false;
     std::vector<SysCtl> hctl;
+    SysCtl* pin_ctl = nullptr;   // pinned bounce buffer of hctl: control-block copies never take the driver's pageable staging path
     std::vector<void*> allocs;
     double* d_noise = nullptr;
     ApjObsScratch obs{};
@@ -70,13 +71,22 @@ static int dev_alloc(apj_engine* e, T** p, size_t count) {
     return APJ_OK;
 }
 
+// Control-block transfers go through PINNED host memory. A pageable cudaMemcpyAsync is staged by the
+// driver and can wait on work of OTHER streams; with several slab ranks on one device (tests) a rank
+// whose kernel spins on a peer would then block that peer's control copy: a deadlock until the timeout.
 static int pull_ctl(apj_engine* e) {
-    APJ_CUDA(e, cudaMemcpyAsync(e->hctl.data(), e->st.ctl, sizeof(SysCtl) * e->hctl.size(), cudaMemcpyDeviceToHost, e->stream));
+    const size_t bytes = sizeof(SysCtl) * e->hctl.size();
+    if (!e->pin_ctl) APJ_CUDA(e, cudaMallocHost(&e->pin_ctl, bytes));
+    APJ_CUDA(e, cudaMemcpyAsync(e->pin_ctl, e->st.ctl, bytes, cudaMemcpyDeviceToHost, e->stream));
     APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(e->hctl.data(), e->pin_ctl, bytes);
     return APJ_OK;
 }
 static int push_ctl(apj_engine* e) {
-    APJ_CUDA(e, cudaMemcpyAsync(e->st.ctl, e->hctl.data(), sizeof(SysCtl) * e->hctl.size(), cudaMemcpyHostToDevice, e->stream));
+    const size_t bytes = sizeof(SysCtl) * e->hctl.size();
+    if (!e->pin_ctl) APJ_CUDA(e, cudaMallocHost(&e->pin_ctl, bytes));
+    memcpy(e->pin_ctl, e->hctl.data(), bytes);
+    APJ_CUDA(e, cudaMemcpyAsync(e->st.ctl, e->pin_ctl, bytes, cudaMemcpyHostToDevice, e->stream));
     APJ_CUDA(e, cudaStreamSynchronize(e->stream));
     return APJ_OK;
 }
@@ -171,9 +181,12 @@ static int maybe_shrink_tile_cap(apj_engine* e) {
 static int check_overflow(apj_engine* e) {
     if (e->st.slab && e->hctl[0].slab_err) {
         const int f = e->hctl[0].slab_err;
-        char b[320];
-        snprintf(b, sizeof b, "slab rank %d/%d:%s%s%s", e->st.rank, e->st.nranks,
-                 (f & 1) ? " a peer rank did not arrive within the timeout;" : "",
+        char b[480], w[160] = "";
+        const int dg = e->hctl[0].slab_diag;
+        if (f & 1) snprintf(w, sizeof w, " (first wait that timed out: %s, missing ranks mask 0x%x)",
+                            (dg >> 16) == 1 ? "step partials" : ((dg >> 16) == 2 ? "rebuild, migrants delivered" : "rebuild, ghost columns"), dg & 0xffff);
+        snprintf(b, sizeof b, "slab rank %d/%d:%s%s%s%s", e->st.rank, e->st.nranks,
+                 (f & 1) ? " a peer rank did not arrive within the timeout" : "", w,
                  (f & 2) ? " a particle crossed more than one slab between rebuilds;" : "",
                  (f & 4) ? " particle / ghost-column / migration capacity exceeded (recreate with a larger capacity);" : "");
         return fail(e, (f & 4) ? APJ_E_OVERFLOW : APJ_E_STATE, b);
@@ -253,7 +266,10 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     st.G = cfg->lanes_per_particle;
     if (st.G == 0) st.G = st.ntot < 150000 ? 4 : (st.ntot < 400000 ? 2 : 1);
     if (st.G != 1 && st.G != 2 && st.G != 4 && st.G != 8) { e->err = "apj_create: lanes_per_particle must be 1, 2, 4 or 8"; return bail(APJ_E_INVALID); }
-    st.tb = st.G == 1 ? 256 : 128;
+#ifndef APJ_TB_G1
+#define APJ_TB_G1 256
+#endif
+    st.tb = st.G == 1 ? APJ_TB_G1 : 128;
     st.ppb = st.tb / st.G;
     st.max_rounds = (st.S / 2 + st.G - 1) / st.G;
     st.max_quads = (st.max_rounds + 3) / 4;
@@ -262,6 +278,13 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     const double rn = cfg->rn > 0 ? cfg->rn : 2.8;
     const double rs = (cfg->rs_factor > 0 ? cfg->rs_factor : 1.5) * rn;
     st.dt = dt; st.rn2 = rn * rn; st.rs2 = rs * rs; st.skin = rs - rn;
+    for (int k = 0; k < APJ_CLASSES; k++) { const double r = rn + (k + 1) * st.skin / APJ_CLASSES; st.cls2[k] = r * r; }
+    st.cls2[APJ_CLASSES - 1] = st.rs2;
+#ifdef APJ_NO_TRUNCATE
+    st.truncate = 0;
+#else
+    st.truncate = 1;
+#endif
     st.seed = cfg->seed;
     e->m = cfg->steps_per_launch > 0 ? cfg->steps_per_launch : 16;
 
@@ -329,6 +352,7 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     A(dev_alloc(e, &st.col_blk, (size_t)cols));
     A(dev_alloc(e, &st.chunk_sums, (size_t)st.n_sys * ((e->max_nbox + apj_scan_chunk_cells() - 1) / apj_scan_chunk_cells())));
     A(dev_alloc(e, &st.cnt, (size_t)st.ntot));
+    A(dev_alloc(e, &st.cntk, (size_t)st.ntot));
     A(dev_alloc(e, &st.boxnew, (size_t)st.ntot));
     A(dev_alloc(e, &st.perm, (size_t)st.ntot));
     A(dev_alloc(e, &st.cell_count, (size_t)cells));
@@ -361,6 +385,7 @@ extern "C" int apj_destroy(apj_engine* e) {
     if (e->group_exec) cudaGraphExecDestroy(e->group_exec);
     for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void* p : e->allocs) cudaFree(p);
+    if (e->pin_ctl) cudaFreeHost(e->pin_ctl);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -512,6 +537,7 @@ extern "C" int apj_set_com(apj_engine* e, int32_t s, const double* com, const do
     if (com) { c.COM[0] = com[0]; c.COM[1] = com[1]; }
     if (com0) { c.COM0[0] = com0[0]; c.COM0[1] = com0[1]; }
     if (com_old) { c.COM_old[0] = com_old[0]; c.COM_old[1] = com_old[1]; }
+    c.trunc_ok = 0;   // the skin-test value no longer bounds the motion since the list build: sweep full lists
     return push_ctl(e);
 }
 extern "C" int apj_get_com(apj_engine* e, int32_t s, double* com, double* com0, double* com_old) {
@@ -549,6 +575,7 @@ extern "C" int apj_mark_origin(apj_engine* e) {
         SysCtl& c = e->hctl[s];
         c.COM[0] = com[2 * s]; c.COM[1] = com[2 * s + 1];
         c.COM0[0] = c.COM_old[0] = c.COM[0]; c.COM0[1] = c.COM_old[1] = c.COM[1];
+        c.trunc_ok = 0;   // x_old moved without a list build: full lists until the next skin-triggered rebuild
     }
     return push_ctl(e);
 }
@@ -626,6 +653,19 @@ extern "C" int apj_get_counters(apj_engine* e, int32_t s, int64_t* o) {
     o[0] = c.step; o[1] = c.reset_counter; o[2] = c.n_rebuilds; o[3] = c.list_max; o[4] = c.overflow;
     o[5] = e->launches; o[6] = c.n_discarded; o[7] = c.nbox;
     return APJ_OK;
+}
+extern "C" int apj_get_sweep_stats(apj_engine* e, int32_t s, double* o) {
+    if (!e || !o || s < 0 || s >= e->st.n_sys) return APJ_E_INVALID;
+    if (int rc = pull_ctl(e)) return rc;
+    const SysCtl& c = e->hctl[s];
+    o[0] = (double)c.n_retried; o[1] = (e->st.truncate && c.trunc_ok) ? 1.0 : 0.0; o[2] = c.skinD; o[3] = c.kmin;
+    return APJ_OK;
+}
+extern "C" int apj_set_sweep_truncation(apj_engine* e, int32_t on) {
+    if (!e) return APJ_E_INVALID;
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->st.truncate = on ? 1 : 0;
+    return build_group_graph(e);   // kernels take DevState by value
 }
 extern "C" int apj_get_tuning(apj_engine* e, int32_t* o) {
     if (!e || !o) return APJ_E_INVALID;

@@ -115,10 +115,13 @@ __global__ void apj_slab_sync_kernel(const DevState st, const int ch) {
     if (lane < st.nranks) apj_st_release_sys(&apj_peer(st, lane, st.mail)->flag[ch][st.rank], seq);
     bool ok = true;
     if (lane < st.nranks && !ctl->slab_err) ok = apj_wait_flag(&st.mail->flag[ch][lane], seq, st.timeout_ns);
-    ok = __all_sync(0xffffffffu, ok);
+    const unsigned missing = __ballot_sync(0xffffffffu, !ok);
     if (lane == 0) {
         ctl->seq[ch] = seq;
-        if (!ok) ctl->slab_err |= 1;
+        if (missing) {
+            ctl->slab_err |= 1;
+            if (!ctl->slab_diag) ctl->slab_diag = ((ch + 1) << 16) | (int)missing;
+        }
     }
 }
 
@@ -475,12 +478,12 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
 // of the {x,y} pieces, then every thread walks the 3x3 cells around its particle (three runs of
 // consecutive tile slots, or nine single rows where y wraps) straight out of shared memory --
 // neighbouring lanes walk the same runs, so the reads are broadcasts. Two passes: count, then
-// write. Entries within BUILD_NEAR of the particle (the first coordination shell, which is what
-// can interact before the next rebuild moves anything by more than the skin) come first, the
-// rest after, each class in slot order: lanes of a warp then agree on the d2 < rn2 branch at
-// almost every list position, and consecutive lanes read nearby slots. The pair SET is what the
-// reference defines (d2 < rs2); the order inside a list is ours.
-constexpr double BUILD_NEAR2 = 3.15 * 3.15;   // rn + half the skin, squared
+// write. Entries are stored in APJ_CLASSES classes of build distance (class k: d < rn + (k+1) *
+// skin / APJ_CLASSES), each class in slot order. Class 0 is the first coordination shell, so lanes
+// of a warp agree on the d2 < rn2 branch at almost every list position; and a step only sweeps the
+// classes that can have come within rn given the skin-test value D (apj_device.cuh, APJ_CLASSES):
+// cntk[] holds the cumulative list length through each class. The pair SET is what the reference
+// defines (d2 < rs2); the order inside a list is ours.
 
 template <bool WRAP, class F>
 __device__ __forceinline__ void for_each_candidate(const TileDesc& sd, const int* __restrict__ start, const int* __restrict__ gs,
@@ -534,11 +537,47 @@ __device__ __forceinline__ void build_lists(const DevState& st, SysCtl* __restri
     const double2 me = sXY[own];
     const int c = st.BOX[gen][g];
     const int cx = c / b, cy = c - cx * b;
+#ifdef APJ_OLD_BUILD
     int n_near = 0, total = 0;
     for_each_candidate<WRAP>(sd, start, gs, w, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int, double d2) {
         total++;
-        if (d2 < BUILD_NEAR2) n_near++;
+        if (d2 < 3.15*3.15) n_near++;
     });
+    const int S = st.S, G = st.G;
+    const int n = min(total, S);
+    unsigned short* __restrict__ out = reinterpret_cast<unsigned short*>(st.list32 + bg * (long long)st.max_quads * st.tb * 4);
+    auto put = [&](int e, unsigned v) {
+        const int w = e >> 1, sub = w % G, kk = w / G;
+        out[(((size_t)(kk >> 2) * st.tb + t * G + sub) * 4 + (kk & 3)) * 2 + (e & 1)] = (unsigned short)v;
+    };
+    int c_near = 0, c_far = n_near;
+    for_each_candidate<WRAP>(sd, start, gs, w, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int s, double d2) {
+        const int e = (d2 < 3.15*3.15) ? c_near++ : c_far++;
+        if (e < S) put(e, (unsigned)s << 4);
+    });
+    if (n & 1) put(n, 0u);
+    st.cnt[g] = n;
+    st.cntk[g] = (unsigned)n * 0x01010101u;
+#else
+    // two passes: count per distance class, then place (classes in order, slot order inside a class)
+    int ncls[APJ_CLASSES];
+#pragma unroll
+    for (int k = 0; k < APJ_CLASSES; k++) ncls[k] = 0;
+    auto cls_of = [&](double d2) {
+        int k = 0;
+#pragma unroll
+        for (int c = 0; c < APJ_CLASSES - 1; c++) if (!(d2 < st.cls2[c])) k = c + 1;
+        return k;
+    };
+    for_each_candidate<WRAP>(sd, start, gs, w, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int, double d2) {
+        const int k = cls_of(d2);
+#pragma unroll
+        for (int c = 0; c < APJ_CLASSES; c++) if (c == k) ncls[c]++;
+    });
+    int total = 0;
+    int cur_[APJ_CLASSES];                              // running write position of each class
+#pragma unroll
+    for (int k = 0; k < APJ_CLASSES; k++) { cur_[k] = total; total += ncls[k]; }
     const int S = st.S, G = st.G;
     const int n = min(total, S);
     // entry e -> word e/2 -> lane (e/2) % G, that lane's word (e/2) / G, half e & 1
@@ -547,13 +586,23 @@ __device__ __forceinline__ void build_lists(const DevState& st, SysCtl* __restri
         const int w = e >> 1, sub = w % G, kk = w / G;
         out[(((size_t)(kk >> 2) * st.tb + t * G + sub) * 4 + (kk & 3)) * 2 + (e & 1)] = (unsigned short)v;
     };
-    int c_near = 0, c_far = n_near;
+    unsigned packed = 0;
+    {
+        int cum = 0;
+#pragma unroll
+        for (int k = 0; k < APJ_CLASSES; k++) { cum += ncls[k]; packed |= (unsigned)min(cum, S) << (8 * k); }
+    }
     for_each_candidate<WRAP>(sd, start, gs, w, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int s, double d2) {
-        const int e = (d2 < BUILD_NEAR2) ? c_near++ : c_far++;
+        const int k = cls_of(d2);
+        int e = 0;
+#pragma unroll
+        for (int c = 0; c < APJ_CLASSES; c++) if (c == k) e = cur_[c]++;
         if (e < S) put(e, (unsigned)s << 4);
     });
     if (n & 1) put(n, 0u);                             // pad the last word with the sentinel
     st.cnt[g] = n;
+    st.cntk[g] = packed;
+#endif
     if (total > S) ctl->overflow |= 1;                 // list capacity exceeded: reported by the host
     if (total > ctl->list_max) atomicMax(&ctl->list_max, total);
 }
@@ -606,6 +655,10 @@ __global__ void apj_finish_rebuild_kernel(const DevState st) {
         ctl->reset_counter += 1;
     }
     ctl->n_rebuilds += 1;
+    // skin-aware sweep length: valid only while x_old is the state the lists were built from
+    ctl->trunc_ok = ctl->save_old ? 1 : 0;
+    ctl->skinD = 0.0;
+    ctl->kmin = 0;
     ctl->save_old = 0;
     ctl->stale = 0;
     ctl->n_own = ctl->n_end - ctl->p0;

@@ -87,7 +87,10 @@ __device__ __forceinline__ void word_terms(PairAcc& a, const double2 me, const d
     if (d21 < rn2) pair_force(a, Ri, dx1, dy1, d21, at1, dCS, dRR);
 }
 
-constexpr int QREG = 3;   // list quads (4 words = 8 entries each) a thread keeps in registers
+#ifndef APJ_QREG
+#define APJ_QREG 3
+#endif
+constexpr int QREG = APJ_QREG;   // list quads (4 words = 8 entries each) a thread keeps in registers
 
 // nw = list words of this lane; q[] = its first QREG quads (loaded before the tile landed);
 // gq = the lane's quad column in global memory (stride TB) for the rare longer lists
@@ -110,11 +113,37 @@ __device__ __forceinline__ void sweep(PairAcc& acc, const int nw, const uint4 (&
     }
 }
 
+// End of a step, one thread per system: a = {sum x_real, sum y_real, top-1, top-2 displacement^2} of the
+// state the step STARTED from; kcls = the distance classes the launch swept.
+__device__ __forceinline__ void apj_commit(SysCtl* __restrict__ ctl, const DevState& st, const double4 a, const int kcls) {
+    const double D = sqrt(a.z) + sqrt(a.w);
+    if (D > st.skin) {                       // jamming.cpp:611
+        ctl->stale = 1;                      // lists too old for the state this step read:
+        ctl->save_old = 1;                   // drop the speculative result, rebuild, re-run
+        ctl->n_discarded += 1;
+    } else if (kcls < APJ_CLASSES - 1 && apj_class_for(D, st.skin) > kcls) {
+        ctl->kmin = apj_class_for(D, st.skin);   // swept too few classes for this state: drop the result, re-run longer
+        ctl->n_retried += 1;
+    } else {
+        ctl->COM[0] = a.x / st.N;            // calculate_COM (jamming.cpp:761-774)
+        ctl->COM[1] = a.y / st.N;
+        ctl->cur ^= 1;
+        ctl->step += 1;
+        ctl->no_self_once = 0;
+        ctl->skinDD = fmax(D - ctl->skinD, 0.0);
+        ctl->skinD = D;
+        ctl->kmin = 0;
+    }
+}
+
 #ifndef APJ_BLOCKS_256
 #define APJ_BLOCKS_256 4
 #endif
+#ifndef APJ_BLOCKS_128
+#define APJ_BLOCKS_128 8
+#endif
 template <int TB, int G, bool INJECT, bool SLAB>
-__global__ void __launch_bounds__(TB, (TB == 256 ? APJ_BLOCKS_256 : 8))
+__global__ void __launch_bounds__(TB, (TB == 256 ? APJ_BLOCKS_256 : APJ_BLOCKS_128))
 apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const int always_full) {
     constexpr int PPB = TB / G;                        // particles per block
     constexpr int EWARPS = (PPB + 31) / 32;            // warps that run the epilogue
@@ -135,6 +164,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     if (blk >= nblk || ctl->stale || step >= ctl->target) return;  // uniform over the system's blocks
 
     const int cur = ctl->cur, gen = ctl->gen;
+    const int kcls = apj_sweep_class(ctl, st);         // distance classes this launch sweeps (0..kcls)
 
     // tile: slot 0 is the sentinel, slots 1.. are the concatenated pieces; three arrays of 16-byte
     // records {x,y}, {cos,sin}, {R,1/R}, each tile_cap+1 records long
@@ -143,32 +173,45 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     double2* __restrict__ sRRp = sCSp + (st.tile_cap + 1);
     double4* __restrict__ sAcc = reinterpret_cast<double4*>(sRRp + (st.tile_cap + 1));   // G > 1 only
 
-    if (t < 16) reinterpret_cast<int*>(&sd)[t] = desc_word;
-    if (t == 0) apj_mbar_init(&s_bar, 1);
+    // Stage the tile: <= 6 pieces x 3 arrays, one TMA bulk copy each. Warp 0 holds the descriptor in
+    // registers (lanes 0..15); lane 3*p + a issues the copy of piece p of array a, so the <= 18 copies
+    // leave in one instruction instead of a serial loop on one thread, and they leave BEFORE the block
+    // barrier that publishes the descriptor to the other warps.
+    if (wid == 0) {
+        if (lane < 16) reinterpret_cast<int*>(&sd)[lane] = desc_word;
+        if (lane == 0) { apj_mbar_init(&s_bar, 1); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+        __syncwarp();
+        const int np = __shfl_sync(0xffffffffu, desc_word, 3) & 0xff;
+        const int mp = lane / 3, arr = lane - mp * 3;
+        int off = 1, my_off = 1, my_len = 0, my_start = 0;
+#pragma unroll
+        for (int q = 0; q < APJ_MAX_PIECES; q++) {
+            const int start = __shfl_sync(0xffffffffu, desc_word, 4 + q);
+            const int len = __shfl_sync(0xffffffffu, desc_word, 4 + APJ_MAX_PIECES + q);
+            if (q < np) {
+                if (q == mp) { my_off = off; my_len = len; my_start = start; }
+                off += len;
+            }
+        }
+        if (lane == 0) apj_mbar_expect_tx(&s_bar, (unsigned)(off - 1) * 48u);
+        __syncwarp();
+        if (mp < np && my_len > 0) {
+            const double2* src = arr == 0 ? st.XY[cur] : (arr == 1 ? st.CS[cur] : st.RR[gen]);
+            double2* dst = arr == 0 ? sXYp : (arr == 1 ? sCSp : sRRp);
+            apj_bulk_g2s(dst + my_off, src + my_start, (unsigned)my_len * 16u, &s_bar);
+        }
+    }
     if (t == 32 % TB) sXYp[0] = make_double2(1e300, 1e300);
     __syncthreads();
 
     const int npieces = sd.info & 0xff;
     const bool wraps = (sd.info & APJ_INFO_WRAPS) != 0;
-
-    if (t == 0) {   // stage the tile: <= 6 pieces x 3 arrays, one TMA bulk copy each
-        int slots = 0;
-        for (int p = 0; p < npieces; p++) slots += sd.plen[p];
-        apj_mbar_expect_tx(&s_bar, (unsigned)slots * 48u);
-        int off = 1;
-        for (int p = 0; p < npieces; p++) {
-            const unsigned bytes = (unsigned)sd.plen[p] * 16u;
-            apj_bulk_g2s(sXYp + off, st.XY[cur] + sd.pstart[p], bytes, &s_bar);
-            apj_bulk_g2s(sCSp + off, st.CS[cur] + sd.pstart[p], bytes, &s_bar);
-            apj_bulk_g2s(sRRp + off, st.RR[gen] + sd.pstart[p], bytes, &s_bar);
-            off += sd.plen[p];
-        }
-    }
+    (void)npieces;
 
     // per-thread loads that do not depend on the tile: in flight while the TMA copies land
     const int p = t / G, sub = t - p * G;              // sweep mapping: G adjacent lanes per particle
     const bool sweeping = p < sd.n;
-    const int n = sweeping ? st.cnt[sd.g0 + p] : 0;
+    const int n = sweeping ? (int)((st.cntk[sd.g0 + p] >> (8 * kcls)) & 0xffu) : 0;
     const int nwords = (n + 1) >> 1;
     const int nw = (nwords - sub + G - 1) / G;         // list words of this lane (<= 0: none)
     const uint4* __restrict__ gq = reinterpret_cast<const uint4*>(st.list32) + bg * (long long)st.max_quads * TB + t;
@@ -387,17 +430,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     }
     if (lane == 0) {
         ctl->ticket = 0u;
-        if (sqrt(a.z) + sqrt(a.w) > st.skin) {   // jamming.cpp:611
-            ctl->stale = 1;                      // lists too old for the state this step read:
-            ctl->save_old = 1;                   // drop the speculative result, rebuild, re-run
-            ctl->n_discarded += 1;
-        } else {
-            ctl->COM[0] = a.x / st.N;            // calculate_COM (jamming.cpp:761-774)
-            ctl->COM[1] = a.y / st.N;
-            ctl->cur = cur ^ 1;
-            ctl->step = step + 1;
-            ctl->no_self_once = 0;
-        }
+        apj_commit(ctl, st, a, kcls);
     }
 }
 
@@ -411,10 +444,11 @@ __global__ void apj_slab_commit_kernel(const DevState st) {
     const unsigned long long ep = ctl->seq[0];
     bool ok = true;
     if (lane < st.nranks && !ctl->slab_err) ok = apj_wait_flag(&st.mail->flag[0][lane], ep + 1, st.timeout_ns);
-    ok = __all_sync(0xffffffffu, ok);
+    const unsigned missing = __ballot_sync(0xffffffffu, !ok);
     if (lane != 0) return;
     ctl->seq[0] = ep + 1;
-    if (!ok || ctl->slab_err) {   // a peer never showed up: stop stepping, the host reports it
+    if (missing || ctl->slab_err) {   // a peer never showed up: stop stepping, the host reports it
+        if (missing && !ctl->slab_diag) ctl->slab_diag = (1 << 16) | (int)missing;
         ctl->slab_err |= 1;
         ctl->target = ctl->step;
         return;
@@ -426,17 +460,7 @@ __global__ void apj_slab_commit_kernel(const DevState st) {
         a.x += b01.x; a.y += b01.y;
         apj_top2_merge(a.z, a.w, b23.x, b23.y);
     }
-    if (sqrt(a.z) + sqrt(a.w) > st.skin) {   // jamming.cpp:611
-        ctl->stale = 1;
-        ctl->save_old = 1;
-        ctl->n_discarded += 1;
-    } else {
-        ctl->COM[0] = a.x / st.N;            // calculate_COM (jamming.cpp:761-774), N of the global box
-        ctl->COM[1] = a.y / st.N;
-        ctl->cur ^= 1;
-        ctl->step += 1;
-        ctl->no_self_once = 0;
-    }
+    apj_commit(ctl, st, a, apj_sweep_class(ctl, st));   // N of the global box; every rank folds the same partials
 }
 
 size_t step_smem_bytes(const DevState& st) {
@@ -476,7 +500,7 @@ void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int a
     else if (st.tb == 128 && st.G == 4) { CALL(128, 4); }                    \
     else if (st.tb == 128 && st.G == 8) { CALL(128, 8); }
 
-int apj_step_blocks_per_sm_limit(int tb) { return tb == 256 ? APJ_BLOCKS_256 : 8; }
+int apj_step_blocks_per_sm_limit(int tb) { return tb == 256 ? APJ_BLOCKS_256 : APJ_BLOCKS_128; }
 
 int apj_configure_kernels(const DevState& st) {
 #define APJ_CFG(TB, G) return configure<TB, G>(st)

@@ -43,7 +43,7 @@ class _State(C.Structure):
 EXPORTS = ["apj_version", "apj_last_error", "apj_create", "apj_destroy", "apj_set_activity", "apj_set_ramp",
            "apj_upload_state", "apj_download_state", "apj_set_com", "apj_get_com", "apj_mark_origin",
            "apj_skip_self_term_once", "apj_step", "apj_step_injected", "apj_force_rebuild", "apj_sync",
-           "apj_get_counters", "apj_get_tuning", "apj_set_reset_counter", "apj_get_geometry", "apj_get_pair_list", "apj_get_cell_lists", "apj_list_stats",
+           "apj_get_counters", "apj_get_sweep_stats", "apj_set_sweep_truncation", "apj_get_tuning", "apj_set_reset_counter", "apj_get_geometry", "apj_get_pair_list", "apj_get_cell_lists", "apj_list_stats",
            "apj_order_orientation", "apj_msd", "apj_fluct_area", "apj_spatial_correlations", "apj_vel_hist",
            "apj_occupancy_hist", "apj_timer_begin", "apj_timer_end", "apj_time_step_kernel",
            # slab mode (bound in slab.py)
@@ -81,6 +81,8 @@ def load_library():
     L.apj_sync.argtypes = [C.c_void_p]
     L.apj_get_counters.argtypes = [C.c_void_p, C.c_int32, _lp]
     L.apj_get_tuning.argtypes = [C.c_void_p, _ip]
+    L.apj_get_sweep_stats.argtypes = [C.c_void_p, C.c_int32, _dp]
+    L.apj_set_sweep_truncation.argtypes = [C.c_void_p, C.c_int32]
     L.apj_set_reset_counter.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
     L.apj_get_geometry.argtypes = [C.c_void_p, C.c_int32, _dp]
     L.apj_get_pair_list.argtypes = [C.c_void_p, C.c_int32, _lp, _ip, C.c_int64, _lp]
@@ -225,6 +227,14 @@ class DeviceEngine:
         self._chk(self.lib.apj_get_counters(self.h, int(system), _p(o, _lp)))
         return dict(step=int(o[0]), resetCounter=int(o[1]), rebuilds=int(o[2]), list_max=int(o[3]), overflow=int(o[4]),
                     launches=int(o[5]), discarded=int(o[6]), nbox=int(o[7]))
+
+    def sweep_stats(self, system=0):
+        o = np.zeros(4, dtype=np.float64)
+        self._chk(self.lib.apj_get_sweep_stats(self.h, int(system), _p(o, _dp)))
+        return dict(retried=int(o[0]), active=bool(o[1]), skinD=float(o[2]), kmin=int(o[3]))
+
+    def set_sweep_truncation(self, on):
+        self._chk(self.lib.apj_set_sweep_truncation(self.h, 1 if on else 0))
 
     def tuning(self):
         o = np.zeros(8, dtype=np.int32)

@@ -278,3 +278,29 @@ def test_full_size_parity_and_properties(N, rho):
     assert np.allclose(np.cos(d["phi"]), d["cosp"], atol=1e-14)
     assert cnt["rebuilds"] >= 1 and cnt["overflow"] == 0 and cnt["step"] == 150
     o.close()
+
+
+@pytest.mark.parametrize("lanes", [1, 4])
+@pytest.mark.parametrize("l_s", [0.05, 0.5])
+def test_skin_aware_sweep_length_is_bit_identical_to_full_sweep(l_s, lanes):
+    """A step sweeps only the list classes that can have come within rn given the skin-test value
+    (apj_device.cuh APJ_CLASSES); the omitted entries all fail d2 < rn2, so trajectories must be
+    BIT-identical to sweeping the full lists -- over many rebuilds, with the same resetCounter."""
+    N, rho, seed, steps = 4096, 0.9, 7, 600
+    o, _ = relaxed_oracle(N, rho, seed=11, l_s=l_s, l_n=0.5)
+    s = o.state()
+    o.close()
+    out = []
+    for on in (1, 0):
+        with device_from_state(s, seed=seed, lanes_per_particle=lanes) as e:
+            e.set_sweep_truncation(on)
+            e.step(steps)
+            st = e.sweep_stats()
+            out.append((e.download(), e.counters(), st))
+    (a, ca, sa), (b, cb, sb) = out
+    assert ca["step"] == cb["step"] == steps
+    assert ca["resetCounter"] == cb["resetCounter"] and ca["resetCounter"] >= 2
+    for f in ("x", "y", "x_real", "y_real", "cosp", "sinp", "vx", "vy", "phi", "x_old", "y_old"):
+        assert np.array_equal(a[f], b[f]), f
+    assert sa["active"] and not sb["active"]           # the shortening was in force in the first run
+    assert sb["retried"] == 0 and sa["retried"] <= steps // 10
