@@ -92,6 +92,7 @@ struct __align__(128) SysCtl {
     int slab_diag;   // first timed-out wait: (channel + 1) << 16 | mask of the ranks that had not arrived
     double skinD, skinDD;
     long long n_retried;   // launches dropped because the sweep length chosen from the previous step's skinD was too short
+    long long n_class[4];  // committed steps per swept class (APJ_CLASSES entries)
     unsigned long long seq[3];   // slab mode sequence numbers: step epochs, rebuild phase A, rebuild phase B
 };
 
@@ -284,6 +285,16 @@ __device__ __forceinline__ void apj_mbar_expect_tx(unsigned long long* bar, unsi
 __device__ __forceinline__ void apj_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(apj_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(apj_smem_addr(bar)) : "memory");
+}
+// L2 prefetch hints (no data reaches the SM): one line / a contiguous range (16-byte granules)
+__device__ __forceinline__ void apj_prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void apj_bulk_prefetch_l2(const void* p, unsigned bytes) {
+    const unsigned long long a = reinterpret_cast<unsigned long long>(p);
+    const unsigned long long a0 = a & ~15ull;
+    const unsigned n = (unsigned)((a + bytes + 15ull - a0) & ~15ull);
+    if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(n) : "memory");
 }
 // `dep` is threaded through the wait as an in/out operand: shared-memory loads whose address is
 // derived from it cannot be scheduled before the barrier completes.

@@ -654,11 +654,13 @@ extern "C" int apj_get_counters(apj_engine* e, int32_t s, int64_t* o) {
     o[5] = e->launches; o[6] = c.n_discarded; o[7] = c.nbox;
     return APJ_OK;
 }
+static_assert(APJ_CLASSES == 4, "apj_get_sweep_stats reports four classes");
 extern "C" int apj_get_sweep_stats(apj_engine* e, int32_t s, double* o) {
     if (!e || !o || s < 0 || s >= e->st.n_sys) return APJ_E_INVALID;
     if (int rc = pull_ctl(e)) return rc;
     const SysCtl& c = e->hctl[s];
     o[0] = (double)c.n_retried; o[1] = (e->st.truncate && c.trunc_ok) ? 1.0 : 0.0; o[2] = c.skinD; o[3] = c.kmin;
+    for (int k = 0; k < APJ_CLASSES; k++) o[4 + k] = (double)c.n_class[k];
     return APJ_OK;
 }
 extern "C" int apj_set_sweep_truncation(apj_engine* e, int32_t on) {

@@ -133,17 +133,29 @@ __device__ __forceinline__ void apj_commit(SysCtl* __restrict__ ctl, const DevSt
         ctl->skinDD = fmax(D - ctl->skinD, 0.0);
         ctl->skinD = D;
         ctl->kmin = 0;
+        ctl->n_class[kcls] += 1;
     }
 }
 
+#ifndef APJ_PF_DIST
+#define APJ_PF_DIST 0   // blocks ahead; 0 = off. Measured on B200 (N = 16M): 444 (3 per SM) cuts the kernel 6 % from a cold L2 (ncu)
+                       // but costs ~1.5 % in steady state, where consecutive launches overlap -- kept as a build option
+#endif
 #ifndef APJ_BLOCKS_256
 #define APJ_BLOCKS_256 4
 #endif
 #ifndef APJ_BLOCKS_128
 #define APJ_BLOCKS_128 8
 #endif
+#ifndef APJ_BLOCKS_192
+#define APJ_BLOCKS_192 6   // 56 registers per thread: 36 warps per SM
+#endif
+#ifndef APJ_BLOCKS_224
+#define APJ_BLOCKS_224 5   // 56 registers per thread: 35 warps per SM
+#endif
+constexpr int apj_blocks_for(int tb) { return tb == 256 ? APJ_BLOCKS_256 : (tb == 224 ? APJ_BLOCKS_224 : (tb == 192 ? APJ_BLOCKS_192 : APJ_BLOCKS_128)); }
 template <int TB, int G, bool INJECT, bool SLAB>
-__global__ void __launch_bounds__(TB, (TB == 256 ? APJ_BLOCKS_256 : APJ_BLOCKS_128))
+__global__ void __launch_bounds__(TB, apj_blocks_for(TB))
 apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const int always_full) {
     constexpr int PPB = TB / G;                        // particles per block
     constexpr int EWARPS = (PPB + 31) / 32;            // warps that run the epilogue
@@ -158,6 +170,18 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     const long long bg = (long long)sys * st.maxblk + blk;
     int desc_word = 0;                                 // fetched alongside ctl: one round trip, not two
     if (t < 16) desc_word = __ldg(reinterpret_cast<const int*>(st.tiles + bg) + t);
+    // Cross-block software prefetch. A step streams ~3 GB through the 126 MB L2, so nothing a block needs
+    // is still cached from the previous step and its head would be two dependent HBM round trips
+    // (descriptor, then tile + lists). Blocks are dispatched in index order, so each block asks L2 for
+    // what block blk + PF will need about one block lifetime later: the last warp reads that block's
+    // descriptor (itself prefetched by block blk - PF) and issues bulk L2 prefetches of its tile pieces,
+    // list quads and per-particle arrays, and touches the descriptor of block blk + 2 PF.
+    constexpr int PF = APJ_PF_DIST;
+    int fdesc = 0;
+    if (PF > 0 && wid == TB / 32 - 1) {
+        if (lane < 16 && blk + PF < st.maxblk) fdesc = __ldg(reinterpret_cast<const int*>(st.tiles + bg + PF) + lane);
+        if (lane == 16 && blk + 2 * PF < st.maxblk) apj_prefetch_l2(st.tiles + bg + 2 * PF);
+    }
     SysCtl* __restrict__ ctl = st.ctl + sys;
     const int nblk = ctl->nblk;
     const long long step = ctl->step;
@@ -237,6 +261,28 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
             const unsigned w = apj_philox_word0((unsigned)id, (unsigned)step, (unsigned)(step >> 32), (unsigned)sys,
                                                 (unsigned)st.seed, (unsigned)(st.seed >> 32));
             u = apj_u32_to_randuni(w);
+        }
+    }
+
+    if (PF > 0 && wid == TB / 32 - 1 && blk + PF < nblk) {   // this warp's own loads are in flight: ask L2 for block blk + PF
+        const int fnp = __shfl_sync(0xffffffffu, fdesc, 3) & 0xff;
+        const int fg0 = __shfl_sync(0xffffffffu, fdesc, 0), fn = __shfl_sync(0xffffffffu, fdesc, 1);
+        const int mp = lane / 3, arr = lane - mp * 3;
+        const int fstart = __shfl_sync(0xffffffffu, fdesc, 4 + (mp < APJ_MAX_PIECES ? mp : 0));
+        const int flen = __shfl_sync(0xffffffffu, fdesc, 4 + APJ_MAX_PIECES + (mp < APJ_MAX_PIECES ? mp : 0));
+        if (lane < 3 * APJ_MAX_PIECES) {
+            if (mp < fnp && flen > 0) {
+                const double2* src = arr == 0 ? st.XY[cur] : (arr == 1 ? st.CS[cur] : st.RR[gen]);
+                apj_bulk_prefetch_l2(src + fstart, (unsigned)flen * 16u);
+            }
+        } else if (fn > 0 && fn <= PPB) {
+            const int a = lane - 3 * APJ_MAX_PIECES;
+            if (a == 0) apj_bulk_prefetch_l2(st.XO[gen] + fg0, (unsigned)fn * 16u);
+            else if (a == 1) apj_bulk_prefetch_l2(st.XR[cur] + fg0, (unsigned)fn * 16u);
+            else if (a == 2) apj_bulk_prefetch_l2(st.ID[gen] + fg0, (unsigned)fn * 4u);
+            else if (a == 3) apj_bulk_prefetch_l2(st.cntk + fg0, (unsigned)fn * 4u);
+            else if (a == 4) apj_bulk_prefetch_l2(reinterpret_cast<const uint4*>(st.list32) + (bg + PF) * (long long)st.max_quads * TB,
+                                                  (unsigned)(st.max_quads < QREG ? st.max_quads : QREG) * TB * 16u);
         }
     }
 
@@ -358,7 +404,8 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     if (SLAB) __syncwarp();   // peer stores of the other lanes are ordered before lane 0's system-scope fence
     if (lane == 0) {
         st.partials[bg] = make_double4(sum_x, sum_y, top1, top2);
-        if (SLAB) __threadfence_system(); else __threadfence();
+        // only blocks that stored into a neighbour's ghost slots need the (expensive) system-scope fence
+        if (SLAB && (sd.info & (APJ_INFO_PUSH_LEFT | APJ_INFO_PUSH_RIGHT))) __threadfence_system(); else __threadfence();
         last = (atomicAdd(gticket + grp, 1u) == (unsigned)gsize - 1u) ? 1u : 0u;
     }
     last = __shfl_sync(0xffffffffu, last, 0);
@@ -495,12 +542,14 @@ void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int a
 
 #define APJ_DISPATCH(CALL)                                                   \
     if (st.tb == 256 && st.G == 1) { CALL(256, 1); }                         \
+    else if (st.tb == 224 && st.G == 1) { CALL(224, 1); }                    \
+    else if (st.tb == 192 && st.G == 1) { CALL(192, 1); }                    \
     else if (st.tb == 128 && st.G == 1) { CALL(128, 1); }                    \
     else if (st.tb == 128 && st.G == 2) { CALL(128, 2); }                    \
     else if (st.tb == 128 && st.G == 4) { CALL(128, 4); }                    \
     else if (st.tb == 128 && st.G == 8) { CALL(128, 8); }
 
-int apj_step_blocks_per_sm_limit(int tb) { return tb == 256 ? APJ_BLOCKS_256 : APJ_BLOCKS_128; }
+int apj_step_blocks_per_sm_limit(int tb) { return apj_blocks_for(tb); }
 
 int apj_configure_kernels(const DevState& st) {
 #define APJ_CFG(TB, G) return configure<TB, G>(st)

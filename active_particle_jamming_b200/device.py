@@ -229,9 +229,9 @@ class DeviceEngine:
                     launches=int(o[5]), discarded=int(o[6]), nbox=int(o[7]))
 
     def sweep_stats(self, system=0):
-        o = np.zeros(4, dtype=np.float64)
+        o = np.zeros(8, dtype=np.float64)
         self._chk(self.lib.apj_get_sweep_stats(self.h, int(system), _p(o, _dp)))
-        return dict(retried=int(o[0]), active=bool(o[1]), skinD=float(o[2]), kmin=int(o[3]))
+        return dict(retried=int(o[0]), active=bool(o[1]), skinD=float(o[2]), kmin=int(o[3]), steps_per_class=[int(v) for v in o[4:8]])
 
     def set_sweep_truncation(self, on):
         self._chk(self.lib.apj_set_sweep_truncation(self.h, 1 if on else 0))

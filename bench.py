@@ -239,9 +239,10 @@ def main():
     e.mark_origin(); e.set_reset_counter(0)
 
     # ---- device-resident throughput
+    smi = ClockSampler(local)                                              # started before the warm-up: nvidia-smi needs ~0.5 s to deliver
     e.step(W)
     c0 = me.counters()
-    smi = ClockSampler(local)
+    sw0 = me.sweep_stats()
     barrier()
     t0w = time.time()
     me.timer_begin()
@@ -250,6 +251,7 @@ def main():
     barrier()
     t1w = time.time()
     c1 = me.counters()
+    sw1 = me.sweep_stats()
     ms = max_over_ranks(ms)
     clocks = smi.window(t0w, t1w)
     n_loc = me.info()["n_own"] if slab else n_loc
@@ -260,6 +262,13 @@ def main():
     n_full, list_max = e.list_stats() if slab else e.list_stats(0)
     barrier()
     kms, committed = me.time_step_kernel(min(max(K, 16), 512))
+    per_rank = None
+    if world > 1:                                                          # per-rank kernel time and share (load balance of the slabs)
+        t = torch.tensor([kms, float(n_loc)], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = {"kernel_ms": [float(v[0]) for v in allt], "particles": [int(v[1]) for v in allt]}
+        kms = max(per_rank["kernel_ms"])
     b_alg = 128.0 + 4.0 * n_full                                           # bytes per particle-step
     peaks = {}
     try:
@@ -271,6 +280,9 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "kernel": "apj_step_kernel", "kernel_ms": kms, "bytes_per_particle_step": b_alg, "n_full": n_full,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
+    if per_rank:
+        roofline["per_rank"] = per_rank
+        roofline["note"] = "per GPU: this rank's particles x bytes / slowest rank's kernel time"
     try:
         roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(a.workload)
     except Exception:
@@ -318,7 +330,9 @@ def main():
                        "lambda_s": l_s, "lambda_n": l_n, "dt": 0.1, "parallelism": parallelism, "relax": [trelax, ttherm],
                        "l2": "state + lists per GPU = %.0f MB, larger than the 126 MB L2: no flush between steps" % (n_loc * reps * (108 + 4 * n_full) / 1e6)
                        if n_loc * reps * 150 > 200e6 else "state fits L2 (%.0f MB): L2-resident by nature of the workload, no flush" % (n_loc * reps * 150 / 1e6),
-                       "rebuilds_in_timed_region": c1["rebuilds"] - c0["rebuilds"], "list_max": list_max, "tuning": me.tuning()},
+                       "rebuilds_in_timed_region": c1["rebuilds"] - c0["rebuilds"], "list_max": list_max, "tuning": me.tuning(),
+                       "sweep": dict(sw1, steps_per_class=[b - a for a, b in zip(sw0["steps_per_class"], sw1["steps_per_class"])],
+                                     retried=sw1["retried"] - sw0["retried"])},
             "roofline": roofline, "e2e": e2e, "gpu_launches": c1["launches"] - c0["launches"], "clocks": clocks}
     smi.stop()
     if rank == 0 and world == 1 and not a.no_cpu:

@@ -118,10 +118,11 @@ int apj_set_reset_counter(apj_engine* e, int32_t system, int64_t value); /* rela
 int apj_get_tuning(apj_engine* e, int32_t* out8);
 /* Skin-aware sweep length (a step sweeps only the list classes that can have come within rn given the
  * skin-test value of newSkinList, jamming.cpp:596-611; verified at commit, results identical to the full
- * sweep). out[4] = {launches dropped and re-run because the chosen length was too short, 1 if the
- * shortening is currently active, current skin-test value sqrt(l1)+sqrt(l2), class floor}.
+ * sweep). out[8] = {launches dropped and re-run because the chosen length was too short, 1 if the
+ * shortening is currently active, current skin-test value sqrt(l1)+sqrt(l2), class floor,
+ * committed steps that swept 1, 2, 3, all 4 of the four build-distance classes}.
  * apj_set_sweep_truncation(e, 0) switches it off (every step sweeps the full lists). */
-int apj_get_sweep_stats(apj_engine* e, int32_t system, double* out4);
+int apj_get_sweep_stats(apj_engine* e, int32_t system, double* out8);
 int apj_set_sweep_truncation(apj_engine* e, int32_t on);
 /* out[5] = {L, Lover2, lp, b, nbox}  (jamming.cpp:99-103) */
 int apj_get_geometry(apj_engine* e, int32_t system, double* out5);
