@@ -130,6 +130,7 @@ struct DevState {
     double dt, rn2, rs2, skin;  // skin = rs - rn (jamming.cpp:611)
     double cls2[APJ_CLASSES];   // (rn + (k+1)*skin/APJ_CLASSES)^2: upper bound of build distance^2 of class k (cls2[last] = rs2)
     int truncate;               // 0 disables the skin-aware sweep length (always the full list)
+    int split_tail;             // 1: step kernel leaves per-block partials, apj_reduce_commit_kernel folds and commits (large systems)
     unsigned long long seed;
     SysCtl* ctl;
     double2* XY[2];

@@ -360,6 +360,14 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     A(dev_alloc(e, &st.cell_cursor, (size_t)cells));
     A(dev_alloc(e, &st.partials, (size_t)st.n_sys * st.maxblk));
     st.maxgrp = (st.maxblk + 31) / 32;
+    // Large systems end the step with a separate fold + commit kernel (apj_step.cu); small ones (phase-diagram
+    // replicas, tests) are launch-bound and keep the commit fused into the step kernel's last block.
+#ifndef APJ_SPLIT_MIN_BLOCKS
+#define APJ_SPLIT_MIN_BLOCKS 4096
+#endif
+    st.split_tail = (st.G == 1 && (long long)st.n_sys * st.maxblk >= APJ_SPLIT_MIN_BLOCKS && st.maxblk <= 1024 * 1024) ? 1 : 0;
+    if (st.G == 1 && (cfg->flags & APJ_FLAG_SPLIT_TAIL) && st.maxblk <= 1024 * 1024) st.split_tail = 1;
+    if (cfg->flags & APJ_FLAG_FUSED_TAIL) st.split_tail = 0;
     A(dev_alloc(e, &st.gpartials, (size_t)st.n_sys * st.maxgrp));
     A(dev_alloc(e, &st.gticket, (size_t)st.n_sys * st.maxgrp));
     A(dev_alloc(e, &e->d_noise, (size_t)st.n_sys * st.N));

@@ -154,7 +154,7 @@ __device__ __forceinline__ void apj_commit(SysCtl* __restrict__ ctl, const DevSt
 #define APJ_BLOCKS_224 5   // 56 registers per thread: 35 warps per SM
 #endif
 constexpr int apj_blocks_for(int tb) { return tb == 256 ? APJ_BLOCKS_256 : (tb == 224 ? APJ_BLOCKS_224 : (tb == 192 ? APJ_BLOCKS_192 : APJ_BLOCKS_128)); }
-template <int TB, int G, bool INJECT, bool SLAB>
+template <int TB, int G, bool INJECT, bool SLAB, bool SPLIT>
 __global__ void __launch_bounds__(TB, apj_blocks_for(TB))
 apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const int always_full) {
     constexpr int PPB = TB / G;                        // particles per block
@@ -396,6 +396,15 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     // warp 0 only from here. Two-level, fixed-order reduction of the per-block partials: the last
     // block of each group of 32 folds its group, the last group to finish folds the groups and
     // commits. Deterministic (membership and order are fixed) and O(sqrt)-deep in the tail.
+    if (SPLIT) {
+        // Large systems: the block only leaves its partial. apj_reduce_commit_kernel (next in the stream)
+        // folds them in a fixed order and commits, so no block ends with a fence + atomic round trip
+        // during which one warp keeps the block's registers and shared memory alive (~10 % of the
+        // resident warp slots at N = 16M).
+        if (SLAB && (sd.info & (APJ_INFO_PUSH_LEFT | APJ_INFO_PUSH_RIGHT))) { __syncwarp(); __threadfence_system(); }
+        if (lane == 0) st.partials[bg] = make_double4(sum_x, sum_y, top1, top2);
+        return;
+    }
     const int grp = blk >> 5, ngrp = (nblk + 31) >> 5;
     const int gsize = min(32, nblk - (grp << 5));
     unsigned* __restrict__ gticket = st.gticket + (long long)sys * st.maxgrp;
@@ -481,6 +490,100 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     }
 }
 
+// Split tail of the step kernel (large systems): deterministic two-level fold of the per-block partials
+// {sum x_real, sum y_real, top-1, top-2 d2}, then the commit (periodic box) or the push of this rank's
+// partial to every rank (slab mode; apj_slab_commit_kernel follows). grid = (chunks, n_sys), RC_TB threads;
+// CTA c folds partials [c*RC_CHUNK, (c+1)*RC_CHUNK): RC_PER consecutive ones per thread, a shuffle tree,
+// the warps in order; the last CTA to finish folds the chunk results the same way.
+constexpr int RC_TB = 256, RC_PER = 4, RC_CHUNK = RC_TB * RC_PER;
+__device__ __forceinline__ double4 rc_block_fold(double4 a, double4* s_w) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+        const double b1 = __shfl_xor_sync(0xffffffffu, a.z, o), b2 = __shfl_xor_sync(0xffffffffu, a.w, o);
+        apj_top2_merge(a.z, a.w, b1, b2);
+    }
+    if (lane == 0) s_w[wid] = a;
+    __syncthreads();
+    if (wid == 0) {
+        a = s_w[0];
+#pragma unroll
+        for (int w = 1; w < RC_TB / 32; w++) {
+            const double4 b = s_w[w];
+            a.x += b.x; a.y += b.y;
+            apj_top2_merge(a.z, a.w, b.z, b.w);
+        }
+    }
+    return a;   // valid in warp 0
+}
+__device__ __forceinline__ double4 rc_load(const double4* p) {
+    const double2 b01 = __ldcg(reinterpret_cast<const double2*>(p)), b23 = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    return make_double4(b01.x, b01.y, b23.x, b23.y);
+}
+__global__ void __launch_bounds__(RC_TB) apj_reduce_commit_kernel(const DevState st) {
+    __shared__ double4 s_w[RC_TB / 32];
+    __shared__ unsigned s_last;
+    const int sys = blockIdx.y, c = blockIdx.x, t = threadIdx.x;
+    SysCtl* __restrict__ ctl = st.ctl + sys;
+    if (ctl->stale || ctl->step >= ctl->target) return;   // the step kernel exited on the same test: nothing to fold
+    const int nblk = ctl->nblk;
+    const int nchunk = (nblk + RC_CHUNK - 1) / RC_CHUNK;
+    if (c >= nchunk) return;
+    const double4* __restrict__ part = st.partials + (long long)sys * st.maxblk;
+    double4* __restrict__ gpart = st.gpartials + (long long)sys * st.maxgrp;
+    double4 a = make_double4(0.0, 0.0, 0.0, 0.0);
+#pragma unroll
+    for (int u = 0; u < RC_PER; u++) {
+        const int k = c * RC_CHUNK + t * RC_PER + u;
+        if (k < nblk) {
+            const double4 b = rc_load(part + k);
+            a.x += b.x; a.y += b.y;
+            apj_top2_merge(a.z, a.w, b.z, b.w);
+        }
+    }
+    a = rc_block_fold(a, s_w);
+    if (t == 0) {
+        gpart[c] = a;
+        __threadfence();
+        s_last = (atomicAdd(&ctl->ticket, 1u) == (unsigned)nchunk - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    a = make_double4(0.0, 0.0, 0.0, 0.0);
+    for (int k = t * RC_PER; k < nchunk; k += RC_TB * RC_PER) {   // nchunk <= RC_CHUNK for every supported size: one pass
+#pragma unroll
+        for (int u = 0; u < RC_PER; u++) {
+            if (k + u < nchunk) {
+                const double4 b = rc_load(gpart + k + u);
+                a.x += b.x; a.y += b.y;
+                apj_top2_merge(a.z, a.w, b.z, b.w);
+            }
+        }
+    }
+    __syncthreads();   // s_w is reused
+    a = rc_block_fold(a, s_w);
+    if (t >= 32) return;
+    const int lane = t;
+    if (st.slab) {
+        if (lane == 0) ctl->ticket = 0u;
+        const unsigned long long ep = ctl->seq[0];
+        if (lane < st.nranks) {
+            SlabMail* m = apj_peer(st, lane, st.mail);
+            m->part[ep & 1][st.rank] = a;
+            __threadfence_system();
+            apj_st_release_sys(&m->flag[0][st.rank], ep + 1);
+        }
+        return;
+    }
+    if (lane == 0) {
+        ctl->ticket = 0u;
+        apj_commit(ctl, st, a, apj_sweep_class(ctl, st));
+    }
+}
+
 // Slab mode: second half of the step. Waits for the partials of all ranks (pushed by their step
 // kernels, see above), folds them in rank order and takes the reference's decision
 // (jamming.cpp:611): commit the speculative step or drop it and rebuild. One warp.
@@ -517,32 +620,42 @@ size_t step_smem_bytes(const DevState& st) {
 template <int TB, int G>
 int configure(const DevState& st) {
     const int bytes = (int)step_smem_bytes(st);
-    if (cudaFuncSetAttribute(apj_step_kernel<TB, G, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(apj_step_kernel<TB, G, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(apj_step_kernel<TB, G, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(apj_step_kernel<TB, G, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+    auto set = [&](auto k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess; };
+    if (!set(apj_step_kernel<TB, G, true, false, false>) || !set(apj_step_kernel<TB, G, false, false, false>) ||
+        !set(apj_step_kernel<TB, G, true, true, false>) || !set(apj_step_kernel<TB, G, false, true, false>)) return -1;
+    if (G == 1 && (!set(apj_step_kernel<TB, 1, true, false, true>) || !set(apj_step_kernel<TB, 1, false, false, true>) ||
+                   !set(apj_step_kernel<TB, 1, true, true, true>) || !set(apj_step_kernel<TB, 1, false, true, true>))) return -1;
     return 0;
+}
+
+template <int TB, int G, bool SPLIT>
+void launch_variant(const DevState& st, cudaStream_t s, const double* noise_by_id, int always_full) {
+    const int grid = st.n_sys * st.maxblk;
+    const size_t smem = step_smem_bytes(st);
+    if (st.slab) {
+        if (noise_by_id) apj_step_kernel<TB, G, true, true, SPLIT><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
+        else apj_step_kernel<TB, G, false, true, SPLIT><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+    } else {
+        if (noise_by_id) apj_step_kernel<TB, G, true, false, SPLIT><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
+        else apj_step_kernel<TB, G, false, false, SPLIT><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+    }
 }
 
 template <int TB, int G>
 void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int always_full) {
-    const int grid = st.n_sys * st.maxblk;
-    const size_t smem = step_smem_bytes(st);
-    if (st.slab) {
-        if (noise_by_id) apj_step_kernel<TB, G, true, true><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
-        else apj_step_kernel<TB, G, false, true><<<grid, TB, smem, s>>>(st, nullptr, always_full);
-        apj_slab_commit_kernel<<<1, 32, 0, s>>>(st);
+    if (G == 1 && st.split_tail) {
+        launch_variant<TB, 1, true>(st, s, noise_by_id, always_full);
+        apj_reduce_commit_kernel<<<dim3((st.maxblk + RC_CHUNK - 1) / RC_CHUNK, st.n_sys), RC_TB, 0, s>>>(st);
     } else {
-        if (noise_by_id) apj_step_kernel<TB, G, true, false><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
-        else apj_step_kernel<TB, G, false, false><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+        launch_variant<TB, G, false>(st, s, noise_by_id, always_full);
     }
+    if (st.slab) apj_slab_commit_kernel<<<1, 32, 0, s>>>(st);
 }
 
 }  // namespace
 
 #define APJ_DISPATCH(CALL)                                                   \
     if (st.tb == 256 && st.G == 1) { CALL(256, 1); }                         \
-    else if (st.tb == 224 && st.G == 1) { CALL(224, 1); }                    \
     else if (st.tb == 192 && st.G == 1) { CALL(192, 1); }                    \
     else if (st.tb == 128 && st.G == 1) { CALL(128, 1); }                    \
     else if (st.tb == 128 && st.G == 2) { CALL(128, 2); }                    \
@@ -562,5 +675,5 @@ void apj_launch_step(const DevState& st, const ApjLaunch& l, const double* noise
 #define APJ_LAUNCH(TB, G) launch<TB, G>(st, l.stream, noise_by_id, always_full)
     APJ_DISPATCH(APJ_LAUNCH)
 #undef APJ_LAUNCH
-    if (l.launch_counter) (*l.launch_counter) += st.slab ? 2 : 1;
+    if (l.launch_counter) (*l.launch_counter) += 1 + (st.slab ? 1 : 0) + ((st.G == 1 && st.split_tail) ? 1 : 0);
 }

@@ -49,6 +49,8 @@ typedef struct apj_config {
 } apj_config;
 
 #define APJ_FLAG_NO_GRAPH 1  /* launch kernels directly instead of through a CUDA graph */
+#define APJ_FLAG_SPLIT_TAIL 2  /* end every step with the separate fold + commit kernel (default: systems of >= 4096 work blocks) */
+#define APJ_FLAG_FUSED_TAIL 4  /* ... or always fold + commit in the step kernel's last block (default: small systems) */
 
 /* Host view of the per-particle fields of `struct Cell` (classes/Cell.h:15-43), 2D. Any
  * pointer may be NULL: on upload a NULL field takes the documented default, on download it is

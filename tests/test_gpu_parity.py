@@ -304,3 +304,28 @@ def test_skin_aware_sweep_length_is_bit_identical_to_full_sweep(l_s, lanes):
         assert np.array_equal(a[f], b[f]), f
     assert sa["active"] and not sb["active"]           # the shortening was in force in the first run
     assert sb["retried"] == 0 and sa["retried"] <= steps // 10
+
+
+def test_split_tail_equals_fused_tail():
+    """Large systems end a step with apj_reduce_commit_kernel instead of the step kernel's last block
+    (APJ_FLAG_SPLIT_TAIL / _FUSED_TAIL force either form). Only the rounding of COM may differ (another
+    fixed summation order), which enters nothing but the skin test: positions are bit-identical, rebuilds
+    fall on the same steps."""
+    N, rho, seed, steps = 6000, 0.9, 5, 400
+    o, _ = relaxed_oracle(N, rho, seed=21, l_s=0.3, l_n=0.5)
+    s = o.state()
+    L = s["L"]
+    o.close()
+    out = []
+    for flags in (2, 4, 2 | 1):
+        with device_from_state(s, seed=seed, lanes_per_particle=1, flags=flags) as e:
+            e.step(1); e.step(steps - 1)
+            out.append((e.download(), e.counters(), e.get_com(0)))
+    (a, ca, ma), (b, cb, mb), (c, cc, mc) = out
+    assert ca["step"] == cb["step"] == cc["step"] == steps
+    assert ca["resetCounter"] == cb["resetCounter"] == cc["resetCounter"] and ca["resetCounter"] >= 2
+    assert ca["launches"] > cb["launches"]                      # one more kernel per step
+    for f in ("x", "y", "x_real", "y_real", "cosp", "sinp", "vx", "vy", "phi", "x_old", "y_old"):
+        assert np.array_equal(a[f], b[f]) and np.array_equal(a[f], c[f]), f
+    assert np.max(np.abs(np.asarray(ma["COM"]) - np.asarray(mb["COM"]))) <= 1e-12 * L
+    assert np.array_equal(np.asarray(ma["COM"]), np.asarray(mc["COM"]))   # graph / direct launches: same bits

@@ -55,8 +55,9 @@ def test_slab_pairs_and_single_step_match_oracle(nranks, lanes):
         o.close()
 
 
-@pytest.mark.parametrize("nranks,lanes,N", [(1, 4, 4096), (2, 4, 4096), (3, 2, 6000), (4, 1, 20000), (8, 1, 40000)])
-def test_slab_free_running_bit_identical_to_periodic(nranks, lanes, N):
+@pytest.mark.parametrize("nranks,lanes,N,flags", [(1, 4, 4096, 0), (2, 4, 4096, 0), (3, 2, 6000, 0), (4, 1, 20000, 0), (8, 1, 40000, 0),
+                                                  (3, 1, 20000, 2)])   # flags 2: split tail (fold + commit kernel) on the slabs
+def test_slab_free_running_bit_identical_to_periodic(nranks, lanes, N, flags):
     """300 Philox steps with frequent rebuilds and migration across slab edges (lambda_s = 0.5): every
     rank count gives the bits of the single-GPU periodic engine."""
     rho, seed = 0.9, 77
@@ -66,7 +67,7 @@ def test_slab_free_running_bit_identical_to_periodic(nranks, lanes, N):
     o.close()
     # 40 relaxation steps leave a few dense clusters of the random start: lists of up to ~50 entries
     e = device_from_state(s, seed=seed, lanes_per_particle=lanes, max_neighbors=64)
-    box = slab_from_state(s, nranks, seed=seed, lanes_per_particle=lanes, max_neighbors=64)
+    box = slab_from_state(s, nranks, seed=seed, lanes_per_particle=lanes, max_neighbors=64, flags=flags)
     try:
         own0 = box.n_own()
         moved = 0
