@@ -869,9 +869,11 @@ extern "C" int apj_time_step_kernel(apj_engine* e, int64_t n, float* mean_ms, in
     std::vector<cudaEvent_t> ev(2 * n);
     for (auto& x : ev) APJ_CUDA(e, cudaEventCreate(&x));
     ApjLaunch l = launcher(e, true);
+    // one target for the whole series (as apj_step does): only the very last step takes the
+    // "store the observables' fields" path, every other launch is the steady-state kernel
+    apj_add_target_kernel<<<(st.n_sys + 63) / 64, 64, 0, e->stream>>>(st.ctl, st.n_sys, n);
+    e->launches++;
     for (int64_t k = 0; k < n; k++) {
-        apj_add_target_kernel<<<(st.n_sys + 63) / 64, 64, 0, e->stream>>>(st.ctl, st.n_sys, 1);
-        e->launches++;
         APJ_CUDA(e, cudaEventRecord(ev[2 * k], e->stream));
         apj_launch_step(st, l, nullptr, 0);
         APJ_CUDA(e, cudaEventRecord(ev[2 * k + 1], e->stream));
@@ -884,10 +886,10 @@ extern "C" int apj_time_step_kernel(apj_engine* e, int64_t n, float* mean_ms, in
     *mean_ms = (float)(tot / n);
     if (int rc = pull_ctl(e)) return rc;
     if (committed) *committed = e->hctl[0].step - step0;
-    // finish any step that was rolled back on the last launch
+    // launches that were dropped (rebuild fired, sweep too short) did not advance the step: finish the series
     long long remaining;
     if (!all_done(e, &remaining)) {
-        for (int a = 0; a < 4 && !all_done(e, &remaining); a++) {
+        for (int a = 0; a < 256 && !all_done(e, &remaining); a++) {
             apj_launch_step(st, l, nullptr, 0);
             apj_launch_rebuild_chain(st, l, e->max_nbox, e->max_b);
             if (int rc = pull_ctl(e)) return rc;

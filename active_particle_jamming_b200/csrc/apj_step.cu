@@ -329,14 +329,46 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
             top1 = apj_d2(ddx, ddy);
         }
 
-        // ---- phi = atan2(y_new, x_new) + CTnoise * randuni()   (jamming.cpp:667) ----
-        double phi = atan2(ay, ax) + ctl->CTnoise * u;
-
-        // ---- Cell::update ----
-        if (phi >= APJ_PI) phi -= APJ_PI2;            // periodicAngles, single wrap (Cell.h:160-166)
-        else if (phi < -APJ_PI) phi += APJ_PI2;
-        double sn, cs;
-        sincos(phi, &sn, &cs);
+        // ---- phi = atan2(y_new, x_new) + CTnoise * randuni()   (jamming.cpp:667), then Cell::update:
+        //      periodicAngles (single wrap, Cell.h:160-166), cosp = cos(phi), sinp = sin(phi) ----
+        const double nz = ctl->CTnoise * u;
+        const bool want_phi = always_full || step + 1 == ctl->target;   // phi itself is only read by observables / downloads
+        double phi = 0.0, sn, cs;
+        const double r2 = ax * ax + ay * ay;
+#ifndef APJ_EXACT_TRIG
+        const double anz = fabs(nz);
+        const bool fast = anz >= 1e-7 && anz <= 3.0 && r2 > 1e-200 && r2 < 1e200;
+#else
+        const bool fast = false;
+#endif
+        if (fast) {
+            // cos and sin of theta + eta by the angle-addition identity, theta = atan2(ay, ax) never formed:
+            // (cos theta, sin theta) = (ax, ay) / r, one rsqrt and one sincos(eta) instead of atan2 + sincos.
+            // Both forms are within ~1e-15 of the exact value (measured 1.2e-15 apart over 1.2e7 samples),
+            // far inside the 1e-12 gate. The reference's wrap uses truncated constants: when theta + eta
+            // leaves [-PI, PI) it shifts phi by PI2 = 6.28318531, i.e. rotates (cos, sin) by PI2 - 2 pi.
+            // Whether it wraps follows from the signs: for eta > 0 (theta >= 0 required) phi >= PI iff
+            // sin(phi) < 0, or cos(phi) < 0 and sin(phi) <= sin(PI); mirrored for eta < 0.
+            double sn_n, cn_n;
+            sincos(nz, &sn_n, &cn_n);
+            const double inv = rsqrt(r2);
+            const double c0 = ax * inv, s0 = ay * inv;
+            cs = c0 * cn_n - s0 * sn_n;
+            sn = s0 * cn_n + c0 * sn_n;
+            constexpr double SIN_PI = 3.5897930298416118e-09;    // sin(3.14159265) evaluated on the double constant
+            constexpr double DPI2 = 2.8204138795420667e-09;      // 6.28318531 (as a double) - 2 pi
+            if (nz > 0.0 && ay >= 0.0 && (sn < 0.0 || (cs < 0.0 && sn <= SIN_PI))) {
+                const double c = cs; cs = c + sn * DPI2; sn = sn - c * DPI2;      // phi -= PI2
+            } else if (nz < 0.0 && ay < 0.0 && (sn > 0.0 || (cs < 0.0 && sn > -SIN_PI))) {
+                const double c = cs; cs = c - sn * DPI2; sn = sn + c * DPI2;      // phi += PI2
+            }
+        }
+        if (!fast || want_phi) {
+            phi = atan2(ay, ax) + nz;
+            if (phi >= APJ_PI) phi -= APJ_PI2;
+            else if (phi < -APJ_PI) phi += APJ_PI2;
+            if (!fast) sincos(phi, &sn, &cs);
+        }
         double CF = ctl->CFself;
         if (ctl->ramp_len > 0) {                      // relax() ramp (jamming.cpp:518)
             const long long t_ = step - ctl->ramp_t0;
@@ -367,7 +399,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
                 apj_peer(st, st.right, st.CS[cur ^ 1])[pg] = make_double2(cs, sn);
             }
         }
-        if (always_full || step + 1 == ctl->target) {   // fields only observables read
+        if (want_phi) {   // fields only observables read
             st.V[gen][g] = make_double2(vx, vy);
             st.PHI[gen][g] = phi;
         }

@@ -164,7 +164,7 @@ int apj_occupancy_hist(apj_engine* e, int64_t* hist50);
 int apj_timer_begin(apj_engine* e);
 int apj_timer_end(apj_engine* e, float* milliseconds);
 /* Per-kernel timing of the fused step kernel: launches n single steps with an event pair around
- * each step-kernel launch and returns the mean duration (ms) of those that committed. */
+ * each launch of the step (step kernel + its fold/commit kernel) and returns the mean duration (ms). */
 int apj_time_step_kernel(apj_engine* e, int64_t n, float* mean_ms, int64_t* committed);
 
 /* ---- slab mode: ONE periodic box over the GPUs of a node (BASELINE config 4) --------
