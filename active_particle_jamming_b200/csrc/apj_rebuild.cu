@@ -537,28 +537,6 @@ __device__ __forceinline__ void build_lists(const DevState& st, SysCtl* __restri
     const double2 me = sXY[own];
     const int c = st.BOX[gen][g];
     const int cx = c / b, cy = c - cx * b;
-#ifdef APJ_OLD_BUILD
-    int n_near = 0, total = 0;
-    for_each_candidate<WRAP>(sd, start, gs, w, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int, double d2) {
-        total++;
-        if (d2 < 3.15*3.15) n_near++;
-    });
-    const int S = st.S, G = st.G;
-    const int n = min(total, S);
-    unsigned short* __restrict__ out = reinterpret_cast<unsigned short*>(st.list32 + bg * (long long)st.max_quads * st.tb * 4);
-    auto put = [&](int e, unsigned v) {
-        const int w = e >> 1, sub = w % G, kk = w / G;
-        out[(((size_t)(kk >> 2) * st.tb + t * G + sub) * 4 + (kk & 3)) * 2 + (e & 1)] = (unsigned short)v;
-    };
-    int c_near = 0, c_far = n_near;
-    for_each_candidate<WRAP>(sd, start, gs, w, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int s, double d2) {
-        const int e = (d2 < 3.15*3.15) ? c_near++ : c_far++;
-        if (e < S) put(e, (unsigned)s << 4);
-    });
-    if (n & 1) put(n, 0u);
-    st.cnt[g] = n;
-    st.cntk[g] = (unsigned)n * 0x01010101u;
-#else
     // two passes: count per distance class, then place (classes in order, slot order inside a class)
     int ncls[APJ_CLASSES];
 #pragma unroll
@@ -602,7 +580,6 @@ __device__ __forceinline__ void build_lists(const DevState& st, SysCtl* __restri
     if (n & 1) put(n, 0u);                             // pad the last word with the sentinel
     st.cnt[g] = n;
     st.cntk[g] = packed;
-#endif
     if (total > S) ctl->overflow |= 1;                 // list capacity exceeded: reported by the host
     if (total > ctl->list_max) atomicMax(&ctl->list_max, total);
 }
