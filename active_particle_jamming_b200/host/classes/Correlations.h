@@ -11,6 +11,7 @@
 #define APJ_HOST_CORRELATIONS_H
 
 #include "../../../include/apj_b200.h"
+#include "Batch.h"
 
 struct Correlations
 {
@@ -37,11 +38,14 @@ struct Correlations
     int np, nc, noBins;
     double norm;
 
-    apj_engine* device = nullptr;      // set by Engine::start()
+    ApjBatch* batch = nullptr;         // set by Engine::start(): the device handle (shared by the replicas of a sweep)
+    int system = 0;                    // this run's system index in the batch
+
+    void bind(ApjBatch* b, int sys) { batch = b; system = sys; b->dv[sys] = dv; }
 
 private:
     void need_device(const char* who) const {
-        if (!device) { fprintf(stderr, "Correlations::%s: no device engine bound (this build has no CPU path)\n", who); exit(717); }
+        if (!batch || !batch->dev) { fprintf(stderr, "Correlations::%s: no device engine bound (this build has no CPU path)\n", who); exit(717); }
     }
 };
 
@@ -63,10 +67,8 @@ inline Correlations::Correlations(double L_, double dens_, double cut, double ti
 inline void Correlations::spatialCorrelations(vector<vector<int>>&, vector<Box>&, vector<Cell>&)
 {
     need_device("spatialCorrelations");
-    vector<double> counts(nc), ori(nc), vel(nc), pair(np);
-    if (apj_spatial_correlations(device, cutoff, counts.data(), ori.data(), vel.data(), pair.data()) != APJ_OK) {
-        fprintf(stderr, "apj_spatial_correlations: %s\n", apj_last_error(device)); exit(719);
-    }
+    const double *counts, *ori, *vel, *pair;                      // apj_spatial_correlations, this system's rows
+    batch->spatial_correlations(system, cutoff, nc, np, &counts, &ori, &vel, &pair);
     for (int k = 0; k < nc; k++) {                    // empty shells give 0/0 = NaN, as in the reference (Q14)
         orientationCorrelation[k] += ori[k]/counts[k];
         velocityCorrelation[k] += vel[k]/counts[k];
@@ -84,8 +86,7 @@ inline void Correlations::autocorrelation(int t, vector<double>& orientation)
 inline void Correlations::velDist(vector<Cell>&)
 {
     need_device("velDist");
-    vector<int64_t> h(noBins);
-    if (apj_vel_hist(device, &dv, h.data()) != APJ_OK) { fprintf(stderr, "apj_vel_hist: %s\n", apj_last_error(device)); exit(719); }
+    const int64_t* h = batch->vel_hist(system);                   // apj_vel_hist
     // the reference adds 1/N per particle; adding count/N per bin differs only in the last bits
     for (int k = 0; k < noBins; k++) velocityDistributionValues[k] += (double)h[k]/(double)N;
 }

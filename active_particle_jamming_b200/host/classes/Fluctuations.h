@@ -5,13 +5,14 @@
 // The O(N) work -- the lens-area sum over all disks for one radius (reference :62-76) and the
 // occupancy histogram (:122-139) -- runs on the GPU (apj_fluct_area, apj_occupancy_hist); this
 // class keeps what is sequential bookkeeping in the reference too: the radius / sample-count
-// state machine and the accumulators. `device` must be set before the first
+// state machine and the accumulators. bind() must be called before the first
 // measurement; the vector<Cell>/vector<Box> arguments are accepted for source compatibility
 // and not read (the live state is in HBM). No CPU path.
 #ifndef APJ_HOST_FLUCTUATIONS_H
 #define APJ_HOST_FLUCTUATIONS_H
 
 #include "../../../include/apj_b200.h"
+#include "Batch.h"
 
 struct Fluctuations
 {
@@ -37,11 +38,14 @@ struct Fluctuations
 
     double Lover2, L;
 
-    apj_engine* device = nullptr;      // set by Engine::start()
+    ApjBatch* batch = nullptr;         // set by Engine::start(): the device handle (shared by the replicas of a sweep)
+    int system = 0;                    // this run's system index in the batch
+
+    void bind(ApjBatch* b, int sys) { batch = b; system = sys; b->radius_ptr[sys] = &current_radius; }
 
 private:
     void need_device(const char* who) const {
-        if (!device) { fprintf(stderr, "Fluctuations::%s: no device engine bound (this build has no CPU path)\n", who); exit(717); }
+        if (!batch || !batch->dev) { fprintf(stderr, "Fluctuations::%s: no device engine bound (this build has no CPU path)\n", who); exit(717); }
     }
 };
 
@@ -60,10 +64,7 @@ inline void Fluctuations::measureFluctuations(vector<Cell>&, vector<double>&, Pr
     need_device("measureFluctuations");
     const double expectedV = dens*PI*current_radius*current_radius;
     if (counter < time_interval) {
-        double V = 0.0;                // total disk area inside the circle of current_radius around COM
-        if (apj_fluct_area(device, &current_radius, &V) != APJ_OK) {
-            fprintf(stderr, "apj_fluct_area: %s\n", apj_last_error(device)); exit(719);
-        }
+        const double V = batch->fluct_area(system, current_radius);   // total disk area inside the circle around COM (apj_fluct_area)
         current_value += (V - expectedV)*(V - expectedV);
     } else {                           // quota reached: flush this radius, grow the circle; no sample on this call
         current_value = sqrt(current_value/(double)counter);
@@ -92,8 +93,7 @@ inline double Fluctuations::overlap(double r, double R, double d)
 inline void Fluctuations::density_distribution(vector<Cell>&, vector<Box>&)
 {
     need_device("density_distribution");
-    int64_t h[50];
-    if (apj_occupancy_hist(device, h) != APJ_OK) { fprintf(stderr, "apj_occupancy_hist: %s\n", apj_last_error(device)); exit(719); }
+    const int64_t* h = batch->occupancy_hist(system);             // apj_occupancy_hist
     for (size_t k = 0; k < distribution.size(); k++) distribution[k] += (double)h[k];
 }
 

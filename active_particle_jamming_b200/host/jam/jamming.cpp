@@ -6,6 +6,12 @@
 // geometry, the cadence of measurements, file output).
 //
 //   jam <fullRunID> <runID> <N> <steps> <lambda_s> <lambda_n> <rho>
+//   jam --sweep <input.txt> [replicas per batch]
+//
+// The second form replaces the reference's PBS job array (code/jam/create-arrays.sh, jamming.sh: one
+// single-core process per line of input.txt): consecutive lines with the same N and step count are
+// run as replicas of ONE device handle (n_systems > 1, BASELINE config 5), each with its own Engine,
+// observers and output tree local_output/<fullRunID>/<runID>/, stepped in lockstep (classes/Batch.h).
 //
 // Environment (additions; the reference hard-codes these at compile time, jamming.cpp:28,36,149):
 //   APJ_OUTPUT_ROOT  root that holds local_output/ (default "./")
@@ -25,6 +31,8 @@
 #include <iostream>
 #include <random>
 #include <string>
+#include <fstream>
+#include <sstream>
 
 using namespace std;
 using namespace std::chrono;
@@ -32,6 +40,7 @@ using namespace std::chrono;
 #include "../classes/Cell.h"
 #include "../classes/Box.h"
 #include "../classes/Print.h"
+#include "../classes/Batch.h"
 #include "../classes/Fluctuations.h"
 #include "../classes/Correlations.h"
 #include "../../../include/apj_b200.h"
@@ -115,15 +124,34 @@ struct Engine
     const double rs2 = rs*rs;
 
     // ---- device side (additions) ----
-    apj_engine* dev = nullptr;
-    void attach_device();               // apj_create + upload of `cell`
+    ApjBatch* batch = nullptr;          // the device handle, shared with the other replicas of a sweep (classes/Batch.h)
+    bool own_batch = false;
+    int sys = 0;                        // this run's system index in the batch
+    apj_engine* dev = nullptr;          // == batch->dev
+    void attach_device();               // single run: apj_create + upload of `cell`
+    static ApjBatch* attach_batch(vector<Engine*>& runs);   // sweep: one handle for all of them
+    static void relax_all(vector<Engine*>& runs);
     void flush();                       // run the steps queued by calculate_next_positions()
     void pull_cells();                  // refresh the host mirror `cell` from HBM
     void pull_cell_lists();             // refresh grid[].CellList (Box::CellList, ascending particle index)
     void pull_verlet_lists();           // refresh cell[].VerletList (half lists, partners j > i)
 
+    // start() in pieces, so that a sweep can run many Engines in lockstep
+    void setup();                       // initCells + topology
+    void open_outputs();                // Print, Fluctuations, Correlations
+    void bind_observers();
+    void tick();                        // one iteration of the measurement loop (start() :207-268)
+    void finish();                      // averages, correlation / density output, summary
+    Print* printer = nullptr;
+    Fluctuations* fluct = nullptr;
+    Correlations* corr = nullptr;
+    int corrCounter = 0;
+    high_resolution_clock::time_point t_begin;
+
 private:
     long int pending = 0;               // steps requested but not yet launched
+    long long requested = 0;            // measurement steps requested so far (the batch runs max over its Engines)
+    long long seen_version = -1;
     bool lists_fresh = false;
     long int rebuilds_seen = 0;
     void check(int rc, const char* what);
@@ -166,7 +194,8 @@ Engine::Engine(string dir, string ID, long int n, long int steps, double l_s, do
 
 Engine::~Engine()
 {
-    if (dev) apj_destroy(dev);
+    delete corr; delete fluct; delete printer;
+    if (own_batch) delete batch;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -235,35 +264,57 @@ void Engine::topology()
 
 void Engine::attach_device()
 {
+    vector<Engine*> one(1, this);
+    attach_batch(one);
+    own_batch = true;
+}
+
+// One handle for all runs of a batch: system s = runs[s]. Per-system box length and activity; the
+// state of every run is uploaded in one call (system-major SoA).
+ApjBatch* Engine::attach_batch(vector<Engine*>& runs)
+{
+    const int S = (int)runs.size(), N = runs[0]->N;
+    ApjBatch* b = new ApjBatch(S);
     apj_config cfg = {};
     cfg.n = N;
-    cfg.n_systems = 1;
+    cfg.n_systems = S;
     const char* d = getenv("APJ_DEVICE");
     cfg.device = d ? atoi(d) : 0;
-    cfg.dt = dt; cfg.rn = rn; cfg.rs_factor = rs/rn;
+    cfg.dt = runs[0]->dt; cfg.rn = runs[0]->rn; cfg.rs_factor = runs[0]->rs/runs[0]->rn;
     cfg.seed = g_seed;
-    int rc = apj_create(&cfg, &L, &dev);
+    vector<double> Ls(S), CF(S), CT(S);
+    for (int s = 0; s < S; s++) { Ls[s] = runs[s]->L; CF[s] = runs[s]->CFself; CT[s] = runs[s]->CTnoise; }
+    int rc = apj_create(&cfg, Ls.data(), &b->dev);
     if (rc != APJ_OK) { cout << "apj_create failed (" << rc << "): " << apj_last_error(NULL) << endl; exit(720); }
-    check(apj_set_activity(dev, &CFself, &CTnoise), "apj_set_activity");
+    b->check(apj_set_activity(b->dev, CF.data(), CT.data()), "apj_set_activity");
 
-    vector<double> x(N), y(N), xr(N), yr(N), x0(N), y0(N), xo(N), yo(N), R(N), phi(N), cp(N), sp(N);
-    vector<int32_t> box(N);
-    for (int i = 0; i < N; i++) {
-        const Cell& c = cell[i];
-        x[i] = c.x[0]; y[i] = c.x[1]; xr[i] = c.x_real[0]; yr[i] = c.x_real[1];
-        x0[i] = c.x0[0]; y0[i] = c.x0[1]; xo[i] = c.x_old[0]; yo[i] = c.x_old[1];
-        R[i] = c.R; phi[i] = c.phi; cp[i] = c.cosp; sp[i] = c.sinp; box[i] = c.box;
-    }
-    apj_state s = {};
-    s.x = x.data(); s.y = y.data(); s.x_real = xr.data(); s.y_real = yr.data(); s.x0 = x0.data(); s.y0 = y0.data();
-    s.x_old = xo.data(); s.y_old = yo.data(); s.R = R.data(); s.phi = phi.data(); s.cosp = cp.data(); s.sinp = sp.data();
-    s.box = box.data();
-    check(apj_upload_state(dev, &s), "apj_upload_state");          // bins and builds the lists too
+    const size_t T = (size_t)S*N;
+    vector<double> x(T), y(T), xr(T), yr(T), x0(T), y0(T), xo(T), yo(T), R(T), phi(T), cp(T), sp(T);
+    vector<int32_t> box(T);
+    for (int s = 0; s < S; s++)
+        for (int i = 0; i < N; i++) {
+            const Cell& c = runs[s]->cell[i];
+            const size_t k = (size_t)s*N + i;
+            x[k] = c.x[0]; y[k] = c.x[1]; xr[k] = c.x_real[0]; yr[k] = c.x_real[1];
+            x0[k] = c.x0[0]; y0[k] = c.x0[1]; xo[k] = c.x_old[0]; yo[k] = c.x_old[1];
+            R[k] = c.R; phi[k] = c.phi; cp[k] = c.cosp; sp[k] = c.sinp; box[k] = c.box;
+        }
+    apj_state st = {};
+    st.x = x.data(); st.y = y.data(); st.x_real = xr.data(); st.y_real = yr.data(); st.x0 = x0.data(); st.y0 = y0.data();
+    st.x_old = xo.data(); st.y_old = yo.data(); st.R = R.data(); st.phi = phi.data(); st.cosp = cp.data(); st.sinp = sp.data();
+    st.box = box.data();
+    b->check(apj_upload_state(b->dev, &st), "apj_upload_state");          // bins and builds the lists too
     // a fresh reference Engine starts with COM = COM_old = 0 and x_new = 0 (reference :139-141, Cell.h:75)
     double zero[2] = {0.0, 0.0};
-    check(apj_set_com(dev, 0, zero, zero, zero), "apj_set_com");
-    check(apj_skip_self_term_once(dev, 1), "apj_skip_self_term_once");
-    lists_fresh = true;
+    for (int s = 0; s < S; s++) b->check(apj_set_com(b->dev, s, zero, zero, zero), "apj_set_com");
+    b->check(apj_skip_self_term_once(b->dev, 1), "apj_skip_self_term_once");
+    b->touch();
+    for (int s = 0; s < S; s++) {
+        Engine* e = runs[s];
+        e->batch = b; e->dev = b->dev; e->sys = s; e->lists_fresh = true;
+        if (e->fluct) e->bind_observers();
+    }
+    return b;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -279,32 +330,35 @@ void Engine::calculate_next_positions()
 
 void Engine::flush()
 {
-    if (pending > 0) {
-        check(apj_step(dev, pending), "apj_step");
-        pending = 0;
-        int64_t c[8];
-        check(apj_get_counters(dev, 0, c), "apj_get_counters");
-        rebuilds_seen = c[1] - resetCounter;
-        resetCounter = c[1];
+    if (pending > 0) { requested += pending; pending = 0; }
+    batch->step_to(requested);          // no-op when another replica of the batch already advanced the device
+    if (seen_version != batch->version) {
         double com[2], com0[2], como[2];
-        check(apj_get_com(dev, 0, com, com0, como), "apj_get_com");
+        long long reset = 0;
+        batch->com(sys, com, com0, como, &reset);
+        rebuilds_seen = reset - resetCounter;
+        resetCounter = reset;
         for (int k = 0; k < NDIM; k++) { COM[k] = com[k]; COM0[k] = com0[k]; COM_old[k] = como[k]; }
+        seen_version = batch->version;
     }
 }
 
 // assignCellsToGrid + buildVerletLists are one on-device chain (counting sort + list build);
-// the pair keeps the reference's two-call protocol (start() :184-185, :245-246).
+// the pair keeps the reference's two-call protocol (start() :184-185, :245-246). In a sweep the
+// chain runs once for all replicas.
 void Engine::assignCellsToGrid()
 {
     flush();
-    check(apj_force_rebuild(dev), "apj_force_rebuild");
+    long long v;
+    batch->force_rebuild_once(v);
     lists_fresh = true;
 }
 
 void Engine::buildVerletLists()
 {
     flush();
-    if (!lists_fresh) check(apj_force_rebuild(dev), "apj_force_rebuild");
+    long long v;
+    if (!lists_fresh) batch->force_rebuild_once(v);
     lists_fresh = true;
 }
 
@@ -319,44 +373,49 @@ void Engine::saveOldPositions() { /* done on the device at every rebuild and by 
 // Passive relaxation, then a linear ramp of the self-propulsion (reference relax :482-525).
 void Engine::relax()
 {
-    const long int trelax = remote ? (long int)(1000.0/dt) : 2000;
+    vector<Engine*> one(1, this);
+    relax_all(one);
+}
+
+void Engine::relax_all(vector<Engine*>& runs)
+{
+    const long int trelax = remote ? (long int)(1000.0/runs[0]->dt) : 2000;
     const long int tthermalize = remote ? 1000000 : 2000;
-    const double final_CF = CFself;
-    double zero = 0.0;
-    flush();
-    check(apj_set_activity(dev, &zero, &CTnoise), "apj_set_activity");
-    check(apj_step(dev, trelax), "apj_step");
-    check(apj_set_activity(dev, &final_CF, &CTnoise), "apj_set_activity");
-    check(apj_set_ramp(dev, tthermalize), "apj_set_ramp");
-    check(apj_step(dev, tthermalize), "apj_step");
-    check(apj_set_ramp(dev, 0), "apj_set_ramp");
-    CFself = final_CF;
-    resetCounter = 0;
-    check(apj_set_reset_counter(dev, 0, 0), "apj_set_reset_counter");
+    ApjBatch* b = runs[0]->batch;
+    const int S = (int)runs.size();
+    vector<double> zero(S, 0.0), CF(S), CT(S);
+    for (int s = 0; s < S; s++) { runs[s]->flush(); CF[s] = runs[s]->CFself; CT[s] = runs[s]->CTnoise; }
+    b->check(apj_set_activity(b->dev, zero.data(), CT.data()), "apj_set_activity");
+    b->check(apj_step(b->dev, trelax), "apj_step");
+    b->check(apj_set_activity(b->dev, CF.data(), CT.data()), "apj_set_activity");
+    b->check(apj_set_ramp(b->dev, tthermalize), "apj_set_ramp");
+    b->check(apj_step(b->dev, tthermalize), "apj_step");
+    b->check(apj_set_ramp(b->dev, 0), "apj_set_ramp");
+    for (int s = 0; s < S; s++) {
+        runs[s]->resetCounter = 0;
+        b->check(apj_set_reset_counter(b->dev, s, 0), "apj_set_reset_counter");
+    }
+    b->touch();
 }
 
 double Engine::calculateOrderParameter()
 {
     flush();
-    double order = 0.0;
-    check(apj_order_orientation(dev, &order, NULL), "apj_order_orientation");
-    return order;
+    return batch->order(sys);           // apj_order_orientation
 }
 
 vector<double> Engine::calculateSystemOrientation()
 {
     flush();
     vector<double> o(NDIM, 0.0);
-    check(apj_order_orientation(dev, NULL, o.data()), "apj_order_orientation");
+    batch->orientation(sys, o.data());
     return o;
 }
 
 double Engine::MSD()
 {
     flush();
-    double msd = 0.0;
-    check(apj_msd(dev, &msd), "apj_msd");
-    return msd;
+    return batch->msd(sys);             // apj_msd
 }
 
 double Engine::delta_norm(double delta)
@@ -372,9 +431,10 @@ double Engine::delta_norm(double delta)
 void Engine::pull_cells()
 {
     flush();
+    const size_t T = (size_t)batch->nsys*N, o = (size_t)sys*N;
     vector<double> f[14];
-    for (auto& v : f) v.resize(N);
-    vector<int32_t> box(N);
+    for (auto& v : f) v.resize(T);
+    vector<int32_t> box(T);
     apj_state s = {};
     s.x = f[0].data(); s.y = f[1].data(); s.x_real = f[2].data(); s.y_real = f[3].data(); s.x0 = f[4].data(); s.y0 = f[5].data();
     s.x_old = f[6].data(); s.y_old = f[7].data(); s.R = f[8].data(); s.phi = f[9].data(); s.cosp = f[10].data(); s.sinp = f[11].data();
@@ -382,10 +442,11 @@ void Engine::pull_cells()
     check(apj_download_state(dev, &s), "apj_download_state");
     for (int i = 0; i < N; i++) {
         Cell& c = cell[i];
-        c.x[0] = f[0][i]; c.x[1] = f[1][i]; c.x_real[0] = f[2][i]; c.x_real[1] = f[3][i];
-        c.x0[0] = f[4][i]; c.x0[1] = f[5][i]; c.x_old[0] = f[6][i]; c.x_old[1] = f[7][i];
-        c.phi = f[9][i]; c.cosp = f[10][i]; c.sinp = f[11][i]; c.vx = f[12][i]; c.vy = f[13][i];
-        c.x_new = c.cosp; c.y_new = c.sinp; c.box = box[i];
+        const size_t k = o + i;
+        c.x[0] = f[0][k]; c.x[1] = f[1][k]; c.x_real[0] = f[2][k]; c.x_real[1] = f[3][k];
+        c.x0[0] = f[4][k]; c.x0[1] = f[5][k]; c.x_old[0] = f[6][k]; c.x_old[1] = f[7][k];
+        c.phi = f[9][k]; c.cosp = f[10][k]; c.sinp = f[11][k]; c.vx = f[12][k]; c.vy = f[13][k];
+        c.x_new = c.cosp; c.y_new = c.sinp; c.box = box[k];
     }
 }
 
@@ -394,7 +455,7 @@ void Engine::pull_cell_lists()
     flush();
     vector<int64_t> off(nbox + 1);
     vector<int32_t> idx(N);
-    check(apj_get_cell_lists(dev, 0, off.data(), idx.data()), "apj_get_cell_lists");
+    check(apj_get_cell_lists(dev, sys, off.data(), idx.data()), "apj_get_cell_lists");
     for (int p = 0; p < nbox; p++) grid[p].CellList.assign(idx.begin() + off[p], idx.begin() + off[p + 1]);
 }
 
@@ -403,9 +464,9 @@ void Engine::pull_verlet_lists()
     flush();
     vector<int64_t> off(N + 1);
     int64_t total = 0;
-    check(apj_get_pair_list(dev, 0, off.data(), NULL, 0, &total), "apj_get_pair_list");
+    check(apj_get_pair_list(dev, sys, off.data(), NULL, 0, &total), "apj_get_pair_list");
     vector<int32_t> idx(total > 0 ? total : 1);
-    check(apj_get_pair_list(dev, 0, off.data(), idx.data(), total, &total), "apj_get_pair_list");
+    check(apj_get_pair_list(dev, sys, off.data(), idx.data(), total, &total), "apj_get_pair_list");
     for (int i = 0; i < N; i++) cell[i].VerletList.assign(idx.begin() + off[i], idx.begin() + off[i + 1]);
 }
 
@@ -427,72 +488,73 @@ void Engine::print_video(Print& printer)
 // Run loop: the reference's cadence (start() :173-283) -- fluctuations every 10 steps (twice on
 // multiples of 100, Q12), order / orientation / COM / MSD every 100, correlations timeAvg times
 // per run, autocorrelation for tCorrelation steps after each of those.
-void Engine::start()
+void Engine::setup()
 {
-    high_resolution_clock::time_point t_begin = high_resolution_clock::now();
-
+    t_begin = high_resolution_clock::now();
     initCells();
     topology();
+}
 
-    Print printer(location, fullRun, run, N, remote);
-    Fluctuations fluct(L, totalSteps, fluct_int, dens);
-    Correlations corr(L, dens, cutoff, tCorrelation, N, CFself);
+void Engine::open_outputs()
+{
+    printer = new Print(location, fullRun, run, N, remote);
+    fluct = new Fluctuations(L, totalSteps, fluct_int, dens);
+    corr = new Correlations(L, dens, cutoff, tCorrelation, N, CFself);
+    if (batch) bind_observers();
+}
 
-    attach_device();
-    fluct.device = dev;
-    corr.device = dev;
+void Engine::bind_observers()
+{
+    fluct->bind(batch, sys);
+    corr->bind(batch, sys);
+}
 
-    assignCellsToGrid();
-    buildVerletLists();
-
-    relax();
-
-    check(apj_mark_origin(dev), "apj_mark_origin");       // x_real = x0 = x, COM0 = COM, saveOldPositions (:191-203)
-    pending = 0;
-
-    int corrCounter = 0;
+void Engine::tick()
+{
     const long int corr_every = totalSteps/timeAvg;
 
-    while (countdown != 0) {
-        calculate_next_positions();
+    calculate_next_positions();
 
-        if (t % fluct_int == 0) { flush(); fluct.measureFluctuations(cell, COM, printer); }
+    if (t % fluct_int == 0) { flush(); fluct->measureFluctuations(cell, COM, *printer); }
 
-        if (t % nSkip == 0) {
-            flush();
-            fluct.measureFluctuations(cell, COM, printer);
-            const double order = calculateOrderParameter();
-            vector<double> orientation = calculateSystemOrientation();
-            const double order2 = order*order;
-            orderAvg += order;
-            order2Avg += order2;
-            order4Avg += order2*order2;
-            printer.print_COM(t, COM);
-            printer.print_order(t, order);
-            printer.print_orientation(t, orientation);
-            printer.print_MSD(t, MSD());
-            if (countdown < film && makevid) print_video(printer);
-        }
-
-        if (corr_every > 0 && t % corr_every == 0 && t != 0) {
-            assignCellsToGrid();
-            buildVerletLists();
-            corr.orientation0 = calculateSystemOrientation();
-            corr.spatialCorrelations(boxPairs, grid, cell);
-            corr.velDist(cell);
-            fluct.density_distribution(cell, grid);
-            corrCounter = 0;
-        }
-
-        if (corrCounter < tCorrelation) {
-            vector<double> orient = calculateSystemOrientation();
-            corr.autocorrelation(corrCounter, orient);
-            corrCounter++;
-        }
-
-        t++;
-        countdown--;
+    if (t % nSkip == 0) {
+        flush();
+        fluct->measureFluctuations(cell, COM, *printer);
+        const double order = calculateOrderParameter();
+        vector<double> orientation = calculateSystemOrientation();
+        const double order2 = order*order;
+        orderAvg += order;
+        order2Avg += order2;
+        order4Avg += order2*order2;
+        printer->print_COM(t, COM);
+        printer->print_order(t, order);
+        printer->print_orientation(t, orientation);
+        printer->print_MSD(t, MSD());
+        if (countdown < film && makevid) print_video(*printer);
     }
+
+    if (corr_every > 0 && t % corr_every == 0 && t != 0) {
+        assignCellsToGrid();
+        buildVerletLists();
+        corr->orientation0 = calculateSystemOrientation();
+        corr->spatialCorrelations(boxPairs, grid, cell);
+        corr->velDist(cell);
+        fluct->density_distribution(cell, grid);
+        corrCounter = 0;
+    }
+
+    if (corrCounter < tCorrelation) {
+        vector<double> orient = calculateSystemOrientation();
+        corr->autocorrelation(corrCounter, orient);
+        corrCounter++;
+    }
+
+    t++;
+    countdown--;
+}
+
+void Engine::finish()
+{
     flush();
 
     orderAvg  /= (double)totalSteps/(double)nSkip;
@@ -501,16 +563,98 @@ void Engine::start()
     binder = 1.0 - order4Avg/(3.0*order2Avg*order2Avg);
     variance = order2Avg - orderAvg*orderAvg;
 
-    corr.printCorrelations(timeAvg, printer);
-    fluct.print_density_distribution(timeAvg, printer);
+    corr->printCorrelations(timeAvg, *printer);
+    fluct->print_density_distribution(timeAvg, *printer);
 
     high_resolution_clock::time_point t_end = high_resolution_clock::now();
     auto duration = duration_cast<seconds>(t_end - t_begin).count();
-    printer.print_summary(run, N, L, t, 1./dt, CFself, CTnoise, dens, duration, resetCounter, binder, orderAvg, variance);
+    printer->print_summary(run, N, L, t, 1./dt, CFself, CTnoise, dens, duration, resetCounter, binder, orderAvg, variance);
+}
+
+void Engine::start()
+{
+    setup();
+    open_outputs();
+    attach_device();
+
+    assignCellsToGrid();
+    buildVerletLists();
+
+    relax();
+
+    check(apj_mark_origin(dev), "apj_mark_origin");       // x_real = x0 = x, COM0 = COM, saveOldPositions (:191-203)
+    batch->touch();
+    pending = 0;
+
+    while (countdown != 0) tick();
+    finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sweep: the reference's job array (create-arrays.sh writes "ID runK N steps lambda_s lambda_n rho"
+// lines into input.txt, jamming.sh starts one process per line) as batched replicas on one GPU.
+struct RunSpec { string full, run; long int n, steps; double l_s, l_n, rho; int line; };
+
+static int run_sweep(const char* path, int per_batch)
+{
+    ifstream in(path);
+    if (!in) { cout << "cannot open " << path << endl; return 2; }
+    vector<RunSpec> specs;
+    string ln;
+    int lineno = 0;
+    while (getline(in, ln)) {
+        lineno++;
+        istringstream is(ln);
+        RunSpec r;
+        if (!(is >> r.full >> r.run >> r.n >> r.steps >> r.l_s >> r.l_n >> r.rho)) {
+            if (ln.find_first_not_of(" \t\r") == string::npos) continue;     // blank line
+            cout << path << ":" << lineno << ": expected <fullRunID> <runID> <N> <steps> <lambda_s> <lambda_n> <rho>" << endl;
+            return 2;
+        }
+        r.line = lineno;
+        specs.push_back(r);
+    }
+    if (per_batch < 1) per_batch = 64;
+    size_t first = 0;
+    while (first < specs.size()) {
+        size_t last = first + 1;                          // consecutive lines of one shape form a batch
+        while (last < specs.size() && last - first < (size_t)per_batch && specs[last].n == specs[first].n && specs[last].steps == specs[first].steps) last++;
+        vector<Engine*> runs;
+        for (size_t k = first; k < last; k++) {
+            const RunSpec& r = specs[k];
+            gen.seed((uint32_t)(g_seed + 7919u*(uint64_t)r.line));       // every line its own initial condition
+            normdist.reset();
+            Engine* e = new Engine(r.full, r.run, r.n, r.steps, r.l_s, r.l_n, r.rho);
+            e->setup();
+            e->open_outputs();
+            runs.push_back(e);
+        }
+        ApjBatch* b = Engine::attach_batch(runs);
+        for (Engine* e : runs) { e->assignCellsToGrid(); e->buildVerletLists(); }
+        Engine::relax_all(runs);
+        b->check(apj_mark_origin(b->dev), "apj_mark_origin");
+        b->touch();
+        while (runs[0]->countdown != 0)
+            for (Engine* e : runs) e->tick();                 // lockstep: the first replica advances the device, the others read
+        for (Engine* e : runs) e->finish();
+        cout << "batch of " << runs.size() << " runs (N = " << specs[first].n << ", " << specs[first].steps << " steps): "
+             << specs[first].run << " .. " << specs[last - 1].run << endl;
+        for (Engine* e : runs) delete e;
+        delete b;
+        first = last;
+    }
+    return 0;
 }
 
 int main(int argc, char* argv[])
 {
+    const char* s = getenv("APJ_SEED");
+    g_seed = s ? strtoull(s, NULL, 10)
+               : (uint64_t)duration_cast<nanoseconds>(high_resolution_clock::now().time_since_epoch()).count();
+    gen.seed((uint32_t)g_seed);
+
+    if (argc >= 3 && string(argv[1]) == "--sweep") return run_sweep(argv[2], argc >= 4 ? atoi(argv[3]) : 64);
+
     if (argc != 8) {
         cout << "Incorrect number of arguments. Need: " << endl
              << "- full run ID" << endl
@@ -523,10 +667,6 @@ int main(int argc, char* argv[])
              << "Program exit status (1)" << endl;
         return 1;
     }
-    const char* s = getenv("APJ_SEED");
-    g_seed = s ? strtoull(s, NULL, 10)
-               : (uint64_t)duration_cast<nanoseconds>(high_resolution_clock::now().time_since_epoch()).count();
-    gen.seed((uint32_t)g_seed);
 
     Engine engine(argv[1], argv[2], atol(argv[3]), atol(argv[4]), atof(argv[5]), atof(argv[6]), atof(argv[7]));
     engine.start();

@@ -69,8 +69,9 @@ def test_driver_has_no_cpu_path(jam, tmp_path):
 def test_host_classes_never_compute_the_hot_path():
     src = open(os.path.join(HOST, "classes", "Cell.h")).read()
     assert "exit(718)" in src                                # Cell::update aborts: the update is the kernel's epilogue
-    drv = open(os.path.join(HOST, "jam", "jamming.cpp")).read()
-    for call in ("apj_step", "apj_force_rebuild", "apj_order_orientation", "apj_msd", "apj_mark_origin"):
+    drv = open(os.path.join(HOST, "jam", "jamming.cpp")).read() + open(os.path.join(HOST, "classes", "Batch.h")).read()
+    for call in ("apj_step", "apj_force_rebuild", "apj_order_orientation", "apj_msd", "apj_mark_origin", "apj_fluct_area",
+                 "apj_spatial_correlations", "apj_vel_hist", "apj_occupancy_hist"):
         assert call in drv
 
 
@@ -146,3 +147,37 @@ int main() {
     assert r.returncode == 0, r.stdout + r.stderr
     inlist, pairs, bad = map(int, r.stdout.split()[:3])
     assert inlist == 1024 and bad == 0 and 7.0 < pairs / 1024 < 9.0      # half-list length ~7.9 at phi = 0.9
+
+
+def test_sweep_rejects_malformed_input(jam, tmp_path):
+    bad = tmp_path / "input.txt"
+    bad.write_text("sw run1 256 100 0.1 0.5\n")                       # six fields instead of seven
+    r = subprocess.run([jam, "--sweep", str(bad)], capture_output=True, text=True, env=dict(os.environ, APJ_OUTPUT_ROOT=str(tmp_path)))
+    assert r.returncode == 2 and "expected <fullRunID> <runID> <N> <steps>" in r.stdout
+    r = subprocess.run([jam, "--sweep", str(tmp_path / "missing.txt")], capture_output=True, text=True)
+    assert r.returncode == 2 and "cannot open" in r.stdout
+
+
+@pytest.mark.gpu
+def test_sweep_runs_input_lines_as_batched_replicas(jam, tmp_path):
+    """jam --sweep input.txt: the reference's job array (create-arrays.sh / jamming.sh, one process per line) as
+    replicas of one device handle. Every line gets the full reference output tree; the physics of each replica
+    follows ITS parameters (order parameter high at low noise, low at high noise), and a replica of a batch agrees
+    statistically with the same line run alone."""
+    g = json.load(open(os.path.join(GOLD, "run_shape.json")))
+    lines = [("runA", 0.3, 0.10, 0.9), ("runB", 0.3, 0.95, 0.9), ("runC", 0.1, 0.10, 0.84), ("runD", 0.3, 0.10, 0.9)]
+    inp = tmp_path / "input.txt"
+    inp.write_text("".join("sweep %s 1024 2000 %g %g %g\n" % l for l in lines) + "sweep runE 576 1000 0.3 0.5 0.9\n")
+    env = dict(os.environ, APJ_OUTPUT_ROOT=str(tmp_path), APJ_SEED="77")
+    r = subprocess.run([jam, "--sweep", str(inp), "3"], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("batch of") == 3                              # 3 + 1 (batch size) + 1 (other shape)
+    order = {}
+    for name, l_s, l_n, rho in lines + [("runE", 0.3, 0.5, 0.9)]:
+        tree = read_tree(os.path.join(str(tmp_path), "local_output", "sweep", name))
+        assert sorted(tree) == sorted(g["shape"]), name                 # the 14 files of a reference run
+        col = np.array([float(l.split("\t")[1]) for l in tree["dat/order.dat"].split("\n")[:-1]])
+        assert len(col) == (1000 if name == "runE" else 2000) // 100 + 1
+        order[name] = col[len(col) // 2:].mean()
+    assert order["runA"] > 0.8 and order["runD"] > 0.8 and order["runB"] < 0.35      # each replica follows its own noise
+    assert abs(order["runA"] - order["runD"]) < 0.15                                 # same point, different batch: same physics
