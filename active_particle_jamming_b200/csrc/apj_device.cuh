@@ -131,6 +131,9 @@ struct DevState {
     double cls2[APJ_CLASSES];   // (rn + (k+1)*skin/APJ_CLASSES)^2: upper bound of build distance^2 of class k (cls2[last] = rs2)
     int truncate;               // 0 disables the skin-aware sweep length (always the full list)
     int split_tail;             // 1: step kernel leaves per-block partials, apj_reduce_commit_kernel folds and commits (large systems)
+    int want_persist;           // APJ_FLAG_PERSIST
+    int persist_grid;           // > 0: blocks of the persistent step kernel (one resident wave; one large system only)
+    int persist_sms;            // SMs of the device (block b of the persistent grid sits in resident slot b / persist_sms)
     unsigned long long seed;
     SysCtl* ctl;
     double2* XY[2];
@@ -316,7 +319,7 @@ struct ApjLaunch { cudaStream_t stream; long long* launch_counter; };
 void apj_launch_step(const DevState& st, const ApjLaunch& l, const double* noise_by_id, int always_full);
 void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nbox, int max_b);
 int apj_rebuild_chain_launches(const DevState& st);
-int apj_configure_kernels(const DevState& st);
+int apj_configure_kernels(DevState& st);   // also sets st.persist_grid
 int apj_configure_rebuild(const DevState& st);
 int apj_step_blocks_per_sm_limit(int tb);   // __launch_bounds__ of the step kernel
 int apj_max_list_capacity();

@@ -155,6 +155,7 @@ static int set_tile_cap(apj_engine* e, int need) {
     if (need > 4094) return fail(e, APJ_E_OVERFLOW, "a work block needs more than 4094 shared-memory slots (density too inhomogeneous for the tile)");
     e->st.tile_cap = e->cfg.tile_slots > 0 ? std::max(e->cfg.tile_slots, need) : best_tile_cap(e->st, need);
     if (apj_configure_kernels(e->st) != 0 || apj_configure_rebuild(e->st) != 0) return fail(e, APJ_E_CUDA, "cannot reserve shared memory for the tile");
+    if ((e->cfg.flags & APJ_FLAG_TINY_GRID) && e->st.persist_grid > 3) e->st.persist_grid = 3;
     if (e->group_exec) { cudaGraphExecDestroy(e->group_exec); e->group_exec = nullptr; }
     return build_group_graph(e);
 }
@@ -368,6 +369,7 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     st.split_tail = (st.G == 1 && (long long)st.n_sys * st.maxblk >= APJ_SPLIT_MIN_BLOCKS && st.maxblk <= 1024 * 1024) ? 1 : 0;
     if (st.G == 1 && (cfg->flags & APJ_FLAG_SPLIT_TAIL) && st.maxblk <= 1024 * 1024) st.split_tail = 1;
     if (cfg->flags & APJ_FLAG_FUSED_TAIL) st.split_tail = 0;
+    st.want_persist = (cfg->flags & APJ_FLAG_PERSIST) ? 1 : 0;
     A(dev_alloc(e, &st.gpartials, (size_t)st.n_sys * st.maxgrp));
     A(dev_alloc(e, &st.gticket, (size_t)st.n_sys * st.maxgrp));
     A(dev_alloc(e, &e->d_noise, (size_t)st.n_sys * st.N));
@@ -375,6 +377,7 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
 #undef A
     if (rc != APJ_OK) return bail(rc);
     if (apj_configure_kernels(st) != 0 || apj_configure_rebuild(st) != 0) { e->err = "apj_create: cannot reserve shared memory for the tile (tile_slots too large?)"; return bail(APJ_E_CUDA); }
+    if ((cfg->flags & APJ_FLAG_TINY_GRID) && st.persist_grid > 3) st.persist_grid = 3;
     if (push_ctl(e) != APJ_OK) return bail(APJ_E_CUDA);
     if (!slab.on || slab.nranks == 1) {      // slab mode: the graph embeds peer addresses, built by apj_slab_ready
         if (build_group_graph(e) != APJ_OK) return bail(APJ_E_CUDA);

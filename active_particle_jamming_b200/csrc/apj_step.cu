@@ -154,7 +154,10 @@ __device__ __forceinline__ void apj_commit(SysCtl* __restrict__ ctl, const DevSt
 #define APJ_BLOCKS_224 5   // 56 registers per thread: 35 warps per SM
 #endif
 constexpr int apj_blocks_for(int tb) { return tb == 256 ? APJ_BLOCKS_256 : (tb == 224 ? APJ_BLOCKS_224 : (tb == 192 ? APJ_BLOCKS_192 : APJ_BLOCKS_128)); }
-template <int TB, int G, bool INJECT, bool SLAB, bool SPLIT>
+// PERSIST (one large system, split tail): the grid is one wave of resident blocks and each block walks the
+// tiles blk, blk + gridDim.x, ... The next tile's descriptor is fetched one tile ahead, so a tile starts
+// with its TMA copies instead of a descriptor round trip, and no block launch sits between two tiles.
+template <int TB, int G, bool INJECT, bool SLAB, bool SPLIT, bool PERSIST>
 __global__ void __launch_bounds__(TB, apj_blocks_for(TB))
 apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const int always_full) {
     constexpr int PPB = TB / G;                        // particles per block
@@ -164,10 +167,11 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ double4 s_red[EWARPS];
 
-    const int sys = blockIdx.x / st.maxblk;
-    const int blk = blockIdx.x - sys * st.maxblk;
+    static_assert(!PERSIST || (SPLIT && G == 1), "the persistent form is the split-tail kernel of one large system");
+    const int sys = PERSIST ? 0 : blockIdx.x / st.maxblk;
+    int blk = PERSIST ? (int)blockIdx.x : (int)(blockIdx.x - sys * st.maxblk);
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const long long bg = (long long)sys * st.maxblk + blk;
+    long long bg = (long long)sys * st.maxblk + blk;
     int desc_word = 0;                                 // fetched alongside ctl: one round trip, not two
     if (t < 16) desc_word = __ldg(reinterpret_cast<const int*>(st.tiles + bg) + t);
     // Cross-block software prefetch. A step streams ~3 GB through the 126 MB L2, so nothing a block needs
@@ -178,7 +182,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     // list quads and per-particle arrays, and touches the descriptor of block blk + 2 PF.
     constexpr int PF = APJ_PF_DIST;
     int fdesc = 0;
-    if (PF > 0 && wid == TB / 32 - 1) {
+    if (PF > 0 && !PERSIST && wid == TB / 32 - 1) {
         if (lane < 16 && blk + PF < st.maxblk) fdesc = __ldg(reinterpret_cast<const int*>(st.tiles + bg + PF) + lane);
         if (lane == 16 && blk + 2 * PF < st.maxblk) apj_prefetch_l2(st.tiles + bg + 2 * PF);
     }
@@ -189,6 +193,20 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
 
     const int cur = ctl->cur, gen = ctl->gen;
     const int kcls = apj_sweep_class(ctl, st);         // distance classes this launch sweeps (0..kcls)
+    int desc_next = 0;                                 // PERSIST: descriptor of this block's next tile, one tile ahead
+    if (PERSIST && t < 16 && blk + (int)gridDim.x < nblk) desc_next = __ldg(reinterpret_cast<const int*>(st.tiles + bg + gridDim.x) + t);
+    unsigned phase = 0;                                // parity of the tile mbarrier (flips per tile)
+    bool first = true;
+#ifndef APJ_PERSIST_STAGGER_NS
+#define APJ_PERSIST_STAGGER_NS 2300
+#endif
+    if (PERSIST && APJ_PERSIST_STAGGER_NS > 0) {
+        // The resident blocks of an SM would otherwise start together and stay in step for most of the launch
+        // (tiles take nearly the same time), all waiting for their tiles at once and all computing at once.
+        // Start them a fraction of a tile time apart, so that one block's tile wait overlaps the others' sweeps.
+        const unsigned slot = blockIdx.x / (unsigned)st.persist_sms;
+        if (slot) __nanosleep(slot * APJ_PERSIST_STAGGER_NS);
+    }
 
     // tile: slot 0 is the sentinel, slots 1.. are the concatenated pieces; three arrays of 16-byte
     // records {x,y}, {cos,sin}, {R,1/R}, each tile_cap+1 records long
@@ -197,13 +215,14 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     double2* __restrict__ sRRp = sCSp + (st.tile_cap + 1);
     double4* __restrict__ sAcc = reinterpret_cast<double4*>(sRRp + (st.tile_cap + 1));   // G > 1 only
 
+  for (;;) {   // one pass per tile (exactly one unless PERSIST)
     // Stage the tile: <= 6 pieces x 3 arrays, one TMA bulk copy each. Warp 0 holds the descriptor in
     // registers (lanes 0..15); lane 3*p + a issues the copy of piece p of array a, so the <= 18 copies
     // leave in one instruction instead of a serial loop on one thread, and they leave BEFORE the block
     // barrier that publishes the descriptor to the other warps.
     if (wid == 0) {
         if (lane < 16) reinterpret_cast<int*>(&sd)[lane] = desc_word;
-        if (lane == 0) { apj_mbar_init(&s_bar, 1); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+        if (lane == 0 && first) { apj_mbar_init(&s_bar, 1); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
         __syncwarp();
         const int np = __shfl_sync(0xffffffffu, desc_word, 3) & 0xff;
         const int mp = lane / 3, arr = lane - mp * 3;
@@ -225,7 +244,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
             apj_bulk_g2s(dst + my_off, src + my_start, (unsigned)my_len * 16u, &s_bar);
         }
     }
-    if (t == 32 % TB) sXYp[0] = make_double2(1e300, 1e300);
+    if (t == 32 % TB && first) sXYp[0] = make_double2(1e300, 1e300);
     __syncthreads();
 
     const int npieces = sd.info & 0xff;
@@ -264,7 +283,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         }
     }
 
-    if (PF > 0 && wid == TB / 32 - 1 && blk + PF < nblk) {   // this warp's own loads are in flight: ask L2 for block blk + PF
+    if (PF > 0 && !PERSIST && wid == TB / 32 - 1 && blk + PF < nblk) {   // this warp's own loads are in flight: ask L2 for block blk + PF
         const int fnp = __shfl_sync(0xffffffffu, fdesc, 3) & 0xff;
         const int fg0 = __shfl_sync(0xffffffffu, fdesc, 0), fn = __shfl_sync(0xffffffffu, fdesc, 1);
         const int mp = lane / 3, arr = lane - mp * 3;
@@ -287,7 +306,8 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     }
 
     unsigned sXY = apj_smem_addr(sXYp);
-    apj_mbar_wait(&s_bar, 0, sXY);
+    apj_mbar_wait(&s_bar, phase, sXY);
+    phase ^= 1u;
     const unsigned dCS = (unsigned)(st.tile_cap + 1) * 16u, dRR = 2u * dCS;
 
     // ---- neighborInteractions ----
@@ -417,13 +437,31 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     if (EWARPS > 1) {
         if (lane == 0) s_red[wid] = make_double4(sum_x, sum_y, top1, top2);
         __syncthreads();       // all EWARPS == all warps of the block when EWARPS > 1 (G == 1 or 2)
-        if (wid != 0) return;
+        if (!PERSIST && wid != 0) return;
+        if (wid == 0) {
 #pragma unroll
-        for (int w = 1; w < EWARPS; w++) {
-            const double4 b = s_red[w];
-            sum_x += b.x; sum_y += b.y;
-            apj_top2_merge(top1, top2, b.z, b.w);
+            for (int w = 1; w < EWARPS; w++) {
+                const double4 b = s_red[w];
+                sum_x += b.x; sum_y += b.y;
+                apj_top2_merge(top1, top2, b.z, b.w);
+            }
         }
+    }
+    if (PERSIST) {
+        // the barrier above also says that every warp is done with this tile's shared memory. Warp 0
+        // leaves the block's partial; then everybody moves to the block's next tile, whose descriptor
+        // arrived while this one was being computed.
+        if (wid == 0) {
+            if (SLAB && (sd.info & (APJ_INFO_PUSH_LEFT | APJ_INFO_PUSH_RIGHT))) { __syncwarp(); __threadfence_system(); }
+            if (lane == 0) st.partials[bg] = make_double4(sum_x, sum_y, top1, top2);
+        }
+        blk += (int)gridDim.x;
+        if (blk >= nblk) return;
+        bg = blk;
+        desc_word = desc_next;
+        if (t < 16 && blk + (int)gridDim.x < nblk) desc_next = __ldg(reinterpret_cast<const int*>(st.tiles + bg + gridDim.x) + t);
+        first = false;
+        continue;
     }
     // warp 0 only from here. Two-level, fixed-order reduction of the per-block partials: the last
     // block of each group of 32 folds its group, the last group to finish folds the groups and
@@ -520,6 +558,8 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         ctl->ticket = 0u;
         apj_commit(ctl, st, a, kcls);
     }
+    return;
+  }   // tile loop
 }
 
 // Split tail of the step kernel (large systems): deterministic two-level fold of the per-block partials
@@ -650,36 +690,49 @@ size_t step_smem_bytes(const DevState& st) {
 }
 
 template <int TB, int G>
-int configure(const DevState& st) {
+int configure(DevState& st) {
     const int bytes = (int)step_smem_bytes(st);
     auto set = [&](auto k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess; };
-    if (!set(apj_step_kernel<TB, G, true, false, false>) || !set(apj_step_kernel<TB, G, false, false, false>) ||
-        !set(apj_step_kernel<TB, G, true, true, false>) || !set(apj_step_kernel<TB, G, false, true, false>)) return -1;
-    if (G == 1 && (!set(apj_step_kernel<TB, 1, true, false, true>) || !set(apj_step_kernel<TB, 1, false, false, true>) ||
-                   !set(apj_step_kernel<TB, 1, true, true, true>) || !set(apj_step_kernel<TB, 1, false, true, true>))) return -1;
+    if (!set(apj_step_kernel<TB, G, true, false, false, false>) || !set(apj_step_kernel<TB, G, false, false, false, false>) ||
+        !set(apj_step_kernel<TB, G, true, true, false, false>) || !set(apj_step_kernel<TB, G, false, true, false, false>)) return -1;
+    st.persist_grid = 0;
+    if (G == 1) {
+        if (!set(apj_step_kernel<TB, 1, true, false, true, false>) || !set(apj_step_kernel<TB, 1, false, false, true, false>) ||
+            !set(apj_step_kernel<TB, 1, true, true, true, false>) || !set(apj_step_kernel<TB, 1, false, true, true, false>)) return -1;
+        if (!set(apj_step_kernel<TB, 1, true, false, true, true>) || !set(apj_step_kernel<TB, 1, false, false, true, true>) ||
+            !set(apj_step_kernel<TB, 1, true, true, true, true>) || !set(apj_step_kernel<TB, 1, false, true, true, true>)) return -1;
+        if (st.split_tail && st.n_sys == 1 && st.want_persist) {   // one wave of resident blocks
+            int dev = 0, sms = 0, nb = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apj_step_kernel<TB, 1, false, false, true, true>, TB, bytes) != cudaSuccess) return -1;
+            st.persist_grid = sms * nb;
+            st.persist_sms = sms;
+        }
+    }
     return 0;
 }
 
-template <int TB, int G, bool SPLIT>
+template <int TB, int G, bool SPLIT, bool PERSIST>
 void launch_variant(const DevState& st, cudaStream_t s, const double* noise_by_id, int always_full) {
-    const int grid = st.n_sys * st.maxblk;
+    const int grid = PERSIST ? st.persist_grid : st.n_sys * st.maxblk;
     const size_t smem = step_smem_bytes(st);
     if (st.slab) {
-        if (noise_by_id) apj_step_kernel<TB, G, true, true, SPLIT><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
-        else apj_step_kernel<TB, G, false, true, SPLIT><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+        if (noise_by_id) apj_step_kernel<TB, G, true, true, SPLIT, PERSIST><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
+        else apj_step_kernel<TB, G, false, true, SPLIT, PERSIST><<<grid, TB, smem, s>>>(st, nullptr, always_full);
     } else {
-        if (noise_by_id) apj_step_kernel<TB, G, true, false, SPLIT><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
-        else apj_step_kernel<TB, G, false, false, SPLIT><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+        if (noise_by_id) apj_step_kernel<TB, G, true, false, SPLIT, PERSIST><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
+        else apj_step_kernel<TB, G, false, false, SPLIT, PERSIST><<<grid, TB, smem, s>>>(st, nullptr, always_full);
     }
 }
 
 template <int TB, int G>
 void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int always_full) {
     if (G == 1 && st.split_tail) {
-        launch_variant<TB, 1, true>(st, s, noise_by_id, always_full);
+        if (st.persist_grid > 0) launch_variant<TB, 1, true, true>(st, s, noise_by_id, always_full);
+        else launch_variant<TB, 1, true, false>(st, s, noise_by_id, always_full);
         apj_reduce_commit_kernel<<<dim3((st.maxblk + RC_CHUNK - 1) / RC_CHUNK, st.n_sys), RC_TB, 0, s>>>(st);
     } else {
-        launch_variant<TB, G, false>(st, s, noise_by_id, always_full);
+        launch_variant<TB, G, false, false>(st, s, noise_by_id, always_full);
     }
     if (st.slab) apj_slab_commit_kernel<<<1, 32, 0, s>>>(st);
 }
@@ -696,7 +749,7 @@ void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int a
 
 int apj_step_blocks_per_sm_limit(int tb) { return apj_blocks_for(tb); }
 
-int apj_configure_kernels(const DevState& st) {
+int apj_configure_kernels(DevState& st) {
 #define APJ_CFG(TB, G) return configure<TB, G>(st)
     APJ_DISPATCH(APJ_CFG)
 #undef APJ_CFG

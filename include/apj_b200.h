@@ -51,6 +51,10 @@ typedef struct apj_config {
 #define APJ_FLAG_NO_GRAPH 1  /* launch kernels directly instead of through a CUDA graph */
 #define APJ_FLAG_SPLIT_TAIL 2  /* end every step with the separate fold + commit kernel (default: systems of >= 4096 work blocks) */
 #define APJ_FLAG_FUSED_TAIL 4  /* ... or always fold + commit in the step kernel's last block (default: small systems) */
+#define APJ_FLAG_PERSIST 16    /* persistent form of the split-tail step kernel (one system): one resident wave of blocks, each walking
+                                * tiles blk, blk + grid, ... with the next descriptor prefetched. Bit-identical; measured 8 % SLOWER than
+                                * one block per tile on B200 at N = 16M, hence opt-in */
+#define APJ_FLAG_TINY_GRID 8   /* tests, with APJ_FLAG_PERSIST: only 3 blocks, so every block walks many tiles */
 
 /* Host view of the per-particle fields of `struct Cell` (classes/Cell.h:15-43), 2D. Any
  * pointer may be NULL: on upload a NULL field takes the documented default, on download it is

@@ -317,11 +317,15 @@ def test_split_tail_equals_fused_tail():
     L = s["L"]
     o.close()
     out = []
-    for flags in (2, 4, 2 | 1):
+    for flags in (2, 4, 2 | 1, 2 | 8 | 16):     # 16 | 8: persistent step kernel on 3 blocks, ~8 tiles per block
         with device_from_state(s, seed=seed, lanes_per_particle=1, flags=flags) as e:
             e.step(1); e.step(steps - 1)
             out.append((e.download(), e.counters(), e.get_com(0)))
-    (a, ca, ma), (b, cb, mb), (c, cc, mc) = out
+    (a, ca, ma), (b, cb, mb), (c, cc, mc), (d, cd, md) = out
+    assert cd["step"] == steps and cd["resetCounter"] == ca["resetCounter"]
+    for f in ("x", "y", "x_real", "y_real", "cosp", "sinp", "vx", "vy", "phi", "x_old", "y_old"):
+        assert np.array_equal(a[f], d[f]), "persistent grid of 3 blocks: " + f
+    assert np.array_equal(np.asarray(ma["COM"]), np.asarray(md["COM"]))
     assert ca["step"] == cb["step"] == cc["step"] == steps
     assert ca["resetCounter"] == cb["resetCounter"] == cc["resetCounter"] and ca["resetCounter"] >= 2
     assert ca["launches"] > cb["launches"]                      # one more kernel per step

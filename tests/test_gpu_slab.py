@@ -56,7 +56,7 @@ def test_slab_pairs_and_single_step_match_oracle(nranks, lanes):
 
 
 @pytest.mark.parametrize("nranks,lanes,N,flags", [(1, 4, 4096, 0), (2, 4, 4096, 0), (3, 2, 6000, 0), (4, 1, 20000, 0), (8, 1, 40000, 0),
-                                                  (3, 1, 20000, 2)])   # flags 2: split tail (fold + commit kernel) on the slabs
+                                                  (3, 1, 20000, 2), (2, 1, 20000, 2 | 8 | 16)])   # flags 2: split tail (fold + commit kernel) on the slabs; 8: persistent kernel on 3 blocks per rank
 def test_slab_free_running_bit_identical_to_periodic(nranks, lanes, N, flags):
     """300 Philox steps with frequent rebuilds and migration across slab edges (lambda_s = 0.5): every
     rank count gives the bits of the single-GPU periodic engine."""
