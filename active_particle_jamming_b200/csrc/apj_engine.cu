@@ -591,6 +591,98 @@ extern "C" int apj_mark_origin(apj_engine* e) {
     return push_ctl(e);
 }
 
+// ---- checkpoint / restart (the reference has none: a killed run is lost) --------------
+// One binary file: header, per-system scalars (step, resetCounter, COM / COM0 / COM_old, activity, ramp, L),
+// then the 14 fp64 fields of apj_state and the box ids, each n_systems * n values in original particle
+// order. Loading re-bins and rebuilds the lists from the stored positions (assignCellsToGrid +
+// buildVerletLists without the skin bookkeeping), keeps x_old / COM_old, and continues the Philox stream
+// at the stored step. The continuation equals the uninterrupted run to rounding (first step <= 1e-12;
+// list order, hence summation order, differs after the fresh rebuild) -- not bit for bit.
+namespace {
+struct CkptHeader { char magic[8]; int64_t n; int32_t n_sys, version; uint64_t seed; double dt, rn2, rs2; };
+struct CkptSys { int64_t step, reset_counter, ramp_len, ramp_t0; double L, CFself, CTnoise, COM[2], COM0[2], COM_old[2]; };
+const char CKPT_MAGIC[8] = {'A', 'P', 'J', 'C', 'K', 'P', 'T', '1'};
+}
+
+extern "C" int apj_save_checkpoint(apj_engine* e, const char* path) {
+    if (!e || !path) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_save_checkpoint: no state uploaded");
+    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_save_checkpoint: slab handle (download the ranks and save a periodic box)");
+    const DevState& st = e->st;
+    const size_t T = (size_t)st.n_sys * st.N;
+    std::vector<double> f[14];
+    for (auto& v : f) v.resize(T);
+    std::vector<int32_t> box(T);
+    apj_state h = {};
+    h.x = f[0].data(); h.y = f[1].data(); h.x_real = f[2].data(); h.y_real = f[3].data(); h.x0 = f[4].data(); h.y0 = f[5].data();
+    h.x_old = f[6].data(); h.y_old = f[7].data(); h.R = f[8].data(); h.phi = f[9].data(); h.cosp = f[10].data(); h.sinp = f[11].data();
+    h.vx = f[12].data(); h.vy = f[13].data(); h.box = box.data();
+    if (int rc = apj_download_state(e, &h)) return rc;          // also refreshes hctl
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(e, APJ_E_INVALID, "apj_save_checkpoint: cannot open the file for writing");
+    CkptHeader hd = {};
+    memcpy(hd.magic, CKPT_MAGIC, 8);
+    hd.n = st.N; hd.n_sys = st.n_sys; hd.version = 1; hd.seed = st.seed; hd.dt = st.dt; hd.rn2 = st.rn2; hd.rs2 = st.rs2;
+    bool ok = fwrite(&hd, sizeof hd, 1, fp) == 1;
+    for (int s = 0; s < st.n_sys && ok; s++) {
+        const SysCtl& c = e->hctl[s];
+        CkptSys cs = {};
+        cs.step = c.step; cs.reset_counter = c.reset_counter; cs.ramp_len = c.ramp_len; cs.ramp_t0 = c.ramp_t0;
+        cs.L = c.L; cs.CFself = c.CFself; cs.CTnoise = c.CTnoise;
+        for (int k = 0; k < 2; k++) { cs.COM[k] = c.COM[k]; cs.COM0[k] = c.COM0[k]; cs.COM_old[k] = c.COM_old[k]; }
+        ok = fwrite(&cs, sizeof cs, 1, fp) == 1;
+    }
+    for (auto& v : f) ok = ok && fwrite(v.data(), sizeof(double), T, fp) == T;
+    ok = ok && fwrite(box.data(), sizeof(int32_t), T, fp) == T;
+    ok = (fclose(fp) == 0) && ok;
+    return ok ? APJ_OK : fail(e, APJ_E_INVALID, "apj_save_checkpoint: short write");
+}
+
+extern "C" int apj_load_checkpoint(apj_engine* e, const char* path) {
+    if (!e || !path) return APJ_E_INVALID;
+    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_load_checkpoint: slab handle");
+    DevState& st = e->st;
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(e, APJ_E_INVALID, "apj_load_checkpoint: cannot open the file");
+    CkptHeader hd;
+    if (fread(&hd, sizeof hd, 1, fp) != 1 || memcmp(hd.magic, CKPT_MAGIC, 8) != 0 || hd.version != 1) {
+        fclose(fp);
+        return fail(e, APJ_E_INVALID, "apj_load_checkpoint: not an APJCKPT1 file");
+    }
+    if (hd.n != st.N || hd.n_sys != st.n_sys || hd.dt != st.dt || hd.rn2 != st.rn2 || hd.rs2 != st.rs2) {
+        fclose(fp);
+        return fail(e, APJ_E_INVALID, "apj_load_checkpoint: the file was written for another shape (n, n_systems, dt, rn, rs)");
+    }
+    std::vector<CkptSys> cs(st.n_sys);
+    bool ok = fread(cs.data(), sizeof(CkptSys), st.n_sys, fp) == (size_t)st.n_sys;
+    for (int s = 0; s < st.n_sys && ok; s++)
+        if (cs[s].L != e->hctl[s].L) { fclose(fp); return fail(e, APJ_E_INVALID, "apj_load_checkpoint: box length differs from the handle's"); }
+    const size_t T = (size_t)st.n_sys * st.N;
+    std::vector<double> f[14];
+    for (auto& v : f) { v.resize(T); ok = ok && fread(v.data(), sizeof(double), T, fp) == T; }
+    std::vector<int32_t> box(T);
+    ok = ok && fread(box.data(), sizeof(int32_t), T, fp) == T;
+    fclose(fp);
+    if (!ok) return fail(e, APJ_E_INVALID, "apj_load_checkpoint: truncated file");
+    apj_state h = {};
+    h.x = f[0].data(); h.y = f[1].data(); h.x_real = f[2].data(); h.y_real = f[3].data(); h.x0 = f[4].data(); h.y0 = f[5].data();
+    h.x_old = f[6].data(); h.y_old = f[7].data(); h.R = f[8].data(); h.phi = f[9].data(); h.cosp = f[10].data(); h.sinp = f[11].data();
+    h.vx = f[12].data(); h.vy = f[13].data(); h.box = box.data();
+    if (int rc = apj_upload_state(e, &h)) return rc;            // re-bins, rebuilds the lists
+    if (int rc = pull_ctl(e)) return rc;
+    for (int s = 0; s < st.n_sys; s++) {
+        SysCtl& c = e->hctl[s];
+        c.step = c.target = cs[s].step; c.reset_counter = cs[s].reset_counter; c.ramp_len = cs[s].ramp_len; c.ramp_t0 = cs[s].ramp_t0;
+        c.CFself = cs[s].CFself; c.CTnoise = cs[s].CTnoise;
+        for (int k = 0; k < 2; k++) { c.COM[k] = cs[s].COM[k]; c.COM0[k] = cs[s].COM0[k]; c.COM_old[k] = cs[s].COM_old[k]; }
+        c.no_self_once = 0;
+        c.trunc_ok = 0;
+    }
+    e->st.seed = hd.seed;                                       // the Philox key travels with the run
+    if (int rc = push_ctl(e)) return rc;
+    return build_group_graph(e);                                // kernels take DevState (seed) by value
+}
+
 extern "C" int apj_sync(apj_engine* e) {
     if (!e) return APJ_E_INVALID;
     APJ_CUDA(e, cudaStreamSynchronize(e->stream));

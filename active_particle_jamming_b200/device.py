@@ -42,7 +42,7 @@ class _State(C.Structure):
 
 EXPORTS = ["apj_version", "apj_last_error", "apj_create", "apj_destroy", "apj_set_activity", "apj_set_ramp",
            "apj_upload_state", "apj_download_state", "apj_set_com", "apj_get_com", "apj_mark_origin",
-           "apj_skip_self_term_once", "apj_step", "apj_step_injected", "apj_force_rebuild", "apj_sync",
+           "apj_skip_self_term_once", "apj_step", "apj_step_injected", "apj_force_rebuild", "apj_sync", "apj_save_checkpoint", "apj_load_checkpoint",
            "apj_get_counters", "apj_get_sweep_stats", "apj_set_sweep_truncation", "apj_get_tuning", "apj_set_reset_counter", "apj_get_geometry", "apj_get_pair_list", "apj_get_cell_lists", "apj_list_stats",
            "apj_order_orientation", "apj_msd", "apj_fluct_area", "apj_spatial_correlations", "apj_vel_hist",
            "apj_occupancy_hist", "apj_timer_begin", "apj_timer_end", "apj_time_step_kernel",
@@ -79,6 +79,8 @@ def load_library():
     L.apj_step_injected.argtypes = [C.c_void_p, _dp]
     L.apj_force_rebuild.argtypes = [C.c_void_p]
     L.apj_sync.argtypes = [C.c_void_p]
+    L.apj_save_checkpoint.argtypes = [C.c_void_p, C.c_char_p]
+    L.apj_load_checkpoint.argtypes = [C.c_void_p, C.c_char_p]
     L.apj_get_counters.argtypes = [C.c_void_p, C.c_int32, _lp]
     L.apj_get_tuning.argtypes = [C.c_void_p, _ip]
     L.apj_get_sweep_stats.argtypes = [C.c_void_p, C.c_int32, _dp]
@@ -221,6 +223,12 @@ class DeviceEngine:
 
     def sync(self):
         self._chk(self.lib.apj_sync(self.h))
+
+    def save_checkpoint(self, path):
+        self._chk(self.lib.apj_save_checkpoint(self.h, os.fsencode(path)))
+
+    def load_checkpoint(self, path):
+        self._chk(self.lib.apj_load_checkpoint(self.h, os.fsencode(path)))
 
     def counters(self, system=0):
         o = np.zeros(8, dtype=np.int64)

@@ -115,6 +115,15 @@ int apj_step_injected(apj_engine* e, const double* noise);
 int apj_force_rebuild(apj_engine* e);
 int apj_sync(apj_engine* e);
 
+/* Checkpoint / restart (an addition: the reference never serialises its state). One binary file with the
+ * per-system scalars (step, resetCounter, COM / COM0 / COM_old, activity, ramp) and every per-particle field
+ * in original particle order. apj_load_checkpoint needs a handle of the same shape (n, n_systems, L, dt, rn,
+ * rs); it restores the Philox key and step, re-bins and rebuilds the lists from the stored positions and keeps
+ * x_old / COM_old, so the continuation follows the uninterrupted run to rounding (not bit for bit: the fresh
+ * lists are ordered differently). Periodic handles only. */
+int apj_save_checkpoint(apj_engine* e, const char* path);
+int apj_load_checkpoint(apj_engine* e, const char* path);
+
 /* out[8] = {step index, resetCounter (jamming.cpp:64), rebuilds incl. forced, longest list,
  *           overflow flag, kernel launches so far, discarded speculative steps, b*b} */
 int apj_get_counters(apj_engine* e, int32_t system, int64_t* out8);

@@ -333,3 +333,46 @@ def test_split_tail_equals_fused_tail():
         assert np.array_equal(a[f], b[f]) and np.array_equal(a[f], c[f]), f
     assert np.max(np.abs(np.asarray(ma["COM"]) - np.asarray(mb["COM"]))) <= 1e-12 * L
     assert np.array_equal(np.asarray(ma["COM"]), np.asarray(mc["COM"]))   # graph / direct launches: same bits
+
+
+def test_checkpoint_restart_continues_the_run(tmp_path):
+    """apj_save_checkpoint / apj_load_checkpoint (an addition; the reference cannot resume): the restored
+    handle holds the stored bits, continues the Philox stream at the stored step, takes its first step within
+    1e-12 of the uninterrupted run and rebuilds on the same steps."""
+    from active_particle_jamming_b200 import DeviceEngine
+    from active_particle_jamming_b200.device import ApjError
+    N, rho = 4096, 0.9
+    o, _ = relaxed_oracle(N, rho, seed=31, l_s=0.3, l_n=0.5)
+    s = o.state()
+    L = s["L"]
+    o.close()
+    path = str(tmp_path / "run.apjckpt")
+    with device_from_state(s, seed=9) as a:
+        a.step(150)
+        a.save_checkpoint(path)
+        ca, da, ma = a.counters(), a.download(), a.get_com(0)
+        a.step(1)
+        d1 = a.download()
+        a.step(200)
+        c2 = a.counters()
+    with DeviceEngine(N, L, seed=4242) as b:                   # another key: the checkpoint's must win
+        b.load_checkpoint(path)
+        cb, db, mb = b.counters(), b.download(), b.get_com(0)
+        assert cb["step"] == ca["step"] == 150 and cb["resetCounter"] == ca["resetCounter"]
+        for f in da:
+            if f != "box":                                     # box ids are re-derived from the positions at load
+                assert np.array_equal(da[f], db[f]), f
+        for k in ("COM", "COM0", "COM_old"):
+            assert np.array_equal(np.asarray(ma[k]), np.asarray(mb[k])), k
+        b.step(1)
+        e1 = b.download()
+        assert np.max(wrapped_abs_diff(e1["x"], d1["x"], L)) <= TOL * L and np.max(wrapped_abs_diff(e1["y"], d1["y"], L)) <= TOL * L
+        assert rel_err(e1["cosp"], d1["cosp"]) <= TOL and rel_err(e1["sinp"], d1["sinp"]) <= TOL      # same noise stream
+        b.step(200)
+        c3 = b.counters()
+        assert c3["step"] == c2["step"] == 351 and abs(c3["resetCounter"] - c2["resetCounter"]) <= 1
+    with DeviceEngine(N // 2, L, seed=1) as c:
+        with pytest.raises(ApjError):
+            c.load_checkpoint(path)                            # another shape
+        with pytest.raises(ApjError):
+            c.load_checkpoint(str(tmp_path / "missing"))
