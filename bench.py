@@ -278,7 +278,8 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = n_loc * reps * b_alg / (kms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "apj_step_kernel", "kernel_ms": kms, "bytes_per_particle_step": b_alg, "n_full": n_full,
+                "frac_of_nominal_8000": achieved / 8000.0,
+                "kernel": "apj_step_kernel (+ apj_reduce_commit_kernel)", "kernel_ms": kms, "bytes_per_particle_step": b_alg, "n_full": n_full,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
     if per_rank:
         roofline["per_rank"] = per_rank
