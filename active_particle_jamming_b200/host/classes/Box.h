@@ -9,20 +9,15 @@
 
 struct Box
 {
-    Box();
+    int serial_index = -1;                                   // p = i + j*b (reference numbering)
+    vector<int> vector_index = vector<int>(NDIM, -1);        // (i, j)
+    vector<double> min = vector<double>(NDIM, 0.0);          // lower corner
+    vector<double> max = vector<double>(NDIM, 0.0);          // upper corner
+    vector<double> center = vector<double>(NDIM, 0.0);
+    vector<int> neighbors = vector<int>(9, 0);               // the 3x3 periodic neighbourhood, 2D
+    vector<int> CellList;                                    // particles in the box, ascending index (on request)
 
-    int serial_index;
-    vector<int> vector_index;
-    vector<double> min, max;
-    vector<double> center;
-    vector<int> neighbors;
-    vector<int> CellList;
+    Box() { CellList.reserve(50); }
 };
-
-inline Box::Box()
-    : serial_index(-1), vector_index(NDIM, -1), min(NDIM, 0), max(NDIM, 0), center(NDIM, 0), neighbors(9, 0)
-{
-    CellList.reserve(50);
-}
 
 #endif
