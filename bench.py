@@ -285,7 +285,9 @@ def main():
         roofline["per_rank"] = per_rank
         roofline["note"] = "per GPU: this rank's particles x bytes / slowest rank's kernel time"
     try:
-        roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(a.workload)
+        # ncu capture of the single-GPU workload (profiles/traffic.json); only that configuration has a measured figure
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(a.workload)
+        roofline["traffic"] = tr if (world == 1 and not a.particles) else None
     except Exception:
         pass
 
