@@ -181,3 +181,51 @@ def test_sweep_runs_input_lines_as_batched_replicas(jam, tmp_path):
         order[name] = col[len(col) // 2:].mean()
     assert order["runA"] > 0.8 and order["runD"] > 0.8 and order["runB"] < 0.35      # each replica follows its own noise
     assert abs(order["runA"] - order["runD"]) < 0.15                                 # same point, different batch: same physics
+
+
+def test_host_topology_and_lattice_match_the_reference_algorithm(tmp_path):
+    """Engine::initCells / Engine::topology are host-side setup (no device): the grid (b, lp, the 3x3 periodic
+    neighbour table in the reference's numbering, jamming.cpp:356-410) must equal the oracle's for the same L, and
+    the lattice must follow the reference's recipe (:285-354): radii 1 + N(0,1)/10, L from the packing fraction with
+    the truncated PI, offset rows, all particles inside the box."""
+    from oracle.pyoracle import OracleSim
+    prog = r'''
+#define main jam_main
+#include "jam/jamming.cpp"
+#undef main
+int main() {
+    gen.seed(11); g_seed = 11;
+    Engine e("probe", "run0", 1024, 100, 0.1, 0.5, 0.9);
+    e.initCells(); e.topology();
+    printf("%.17g %d %d %.17g\n", e.L, e.b, e.nbox, e.lp);
+    for (int p = 0; p < e.nbox; p++) { for (int k = 0; k < 9; k++) printf("%d ", e.grid[p].neighbors[k]); printf("\n"); }
+    double sr = 0, sr2 = 0, area = 0; int outside = 0;
+    for (int i = 0; i < e.N; i++) {
+        const Cell& c = e.cell[i];
+        sr += c.R; sr2 += c.R*c.R; area += c.R*c.R;
+        if (c.x[0] < -e.Lover2 || c.x[0] >= e.Lover2 || c.x[1] < -e.Lover2 || c.x[1] >= e.Lover2) outside++;
+        if (fabs(c.cosp - cos(c.phi)) > 1e-15 || fabs(c.Rinv*c.R - 1.0) > 1e-15) outside += 1000;
+    }
+    printf("%.17g %.17g %.17g %d\n", sr/e.N, sr2/e.N, area, outside);
+    return 0;
+}'''
+    src = tmp_path / "topo.cpp"
+    src.write_text(prog)
+    from active_particle_jamming_b200 import _build
+    exe = str(tmp_path / "topo")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", HOST, str(src), "-o", exe, "-L" + os.path.dirname(_build.LIB), "-lapj_b200",
+                    "-Wl,-rpath," + os.path.dirname(_build.LIB)], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().split("\n")
+    L, b, nbox, lp = float(lines[0].split()[0]), int(lines[0].split()[1]), int(lines[0].split()[2]), float(lines[0].split()[3])
+    nb = np.array([[int(v) for v in l.split()] for l in lines[1:1 + nbox]])
+    mean_r, mean_r2, area, outside = lines[1 + nbox].split()
+    o = OracleSim(1024, L, 0.9)
+    o.topology()
+    sc = o.scalars()
+    assert (b, nbox) == (int(sc["b"]), int(sc["nbox"])) and lp == sc["lp"]
+    assert np.array_equal(nb, o.box_neighbors())                       # same table, same numbering
+    o.close()
+    assert L == np.sqrt(3.14159265 * float(area) / 0.9)                # jamming.cpp:305, truncated PI
+    assert abs(float(mean_r) - 1.0) < 0.02 and abs(float(mean_r2) - 1.01) < 0.03 and int(outside) == 0
