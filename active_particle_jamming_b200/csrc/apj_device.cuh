@@ -314,8 +314,21 @@ __device__ __forceinline__ void apj_mbar_wait(unsigned long long* bar, unsigned 
     }
 }
 
+// Staging planes of the host <-> device state hand-over (apj_state_io.cu): the 14 fp64 fields of apj_state
+// in its order (x, y, x_real, y_real, x0, y0, x_old, y_old, R, phi, cosp, sinp, vx, vy), box ids, particle
+// ids (slab upload) and an error flag (1: a radius is not positive, 2: a particle id is out of range).
+struct ApjStage {
+    double* f[14];
+    int* box;
+    int* ids;
+    int* flag;
+};
+
 // host-side launchers (one per .cu)
 struct ApjLaunch { cudaStream_t stream; long long* launch_counter; };
+void apj_launch_pack(const DevState& st, cudaStream_t s, const ApjStage& sg, unsigned present, long long n, int slab);
+void apj_launch_unpack(const DevState& st, cudaStream_t s, const ApjStage& sg, unsigned want, int by_id);
+void apj_launch_checksum(const DevState& st, cudaStream_t s, unsigned long long* out);
 void apj_launch_step(const DevState& st, const ApjLaunch& l, const double* noise_by_id, int always_full);
 void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nbox, int max_b);
 int apj_rebuild_chain_launches(const DevState& st);

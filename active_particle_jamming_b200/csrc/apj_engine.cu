@@ -33,6 +33,11 @@ struct apj_engine {
     SysCtl* pin_ctl = nullptr;   // pinned bounce buffer of hctl: control-block copies never take the driver's pageable staging path
     std::vector<void*> allocs;
     double* d_noise = nullptr;
+    // host <-> device state hand-over (apj_state_io.cu): staging planes in HBM, grown on demand and kept
+    void* stage_mem = nullptr;
+    size_t stage_n = 0;
+    ApjStage stage{};
+    int* pin_small = nullptr;    // pinned scratch for small read-backs (flags, checksums)
     ApjObsScratch obs{};
     std::string err;
     // slab mode
@@ -171,6 +176,39 @@ static int repair_tile_overflow(apj_engine* e, int* repaired) {
     *repaired = 1;
     return push_ctl(e);
 }
+// A Verlet list longer than the capacity S leaves the system stale (apj_finish_rebuild_kernel commits nothing), so
+// no step ever runs on truncated lists: the list storage is re-allocated for the longest list seen (+25 %) and the
+// chain is run again. The reference's std::vector lists are unbounded (jamming.cpp:550-585); the bound here is
+// the 96 entries the 16-bit tile-slot encoding and the register-held quads are built for. Periodic handles only:
+// slab ranks launch in lockstep, there the overflow is reported (check_overflow) and the caller re-creates.
+static void set_list_capacity(DevState& st, int S) {
+    st.S = S;
+    st.max_rounds = (st.S / 2 + st.G - 1) / st.G;
+    st.max_quads = (st.max_rounds + 3) / 4;
+}
+static int repair_list_overflow(apj_engine* e, int* repaired) {
+    if (e->st.slab) return APJ_OK;
+    int need = 0;
+    for (auto& c : e->hctl) if (c.overflow & 1) need = std::max(need, c.list_max);
+    if (!need) return APJ_OK;
+    if (need > apj_max_list_capacity()) return APJ_OK;   // beyond what the layout holds: check_overflow reports it
+    DevState& st = e->st;
+    const int S = std::min(apj_max_list_capacity(), (need + need / 4 + 3) / 2 * 2);
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    set_list_capacity(st, S);
+    unsigned* fresh = nullptr;
+    const size_t words = (size_t)st.n_sys * st.maxblk * st.max_quads * 4 * st.tb;
+    APJ_CUDA(e, cudaMalloc(&fresh, words * sizeof(unsigned)));
+    APJ_CUDA(e, cudaMemsetAsync(fresh, 0, words * sizeof(unsigned), e->stream));
+    e->allocs.erase(std::remove(e->allocs.begin(), e->allocs.end(), (void*)st.list32), e->allocs.end());
+    cudaFree(st.list32);
+    st.list32 = fresh;
+    e->allocs.push_back(fresh);
+    for (auto& c : e->hctl) { c.overflow &= ~1; c.list_max = 0; }
+    if (int rc = push_ctl(e)) return rc;
+    *repaired = 1;
+    return build_group_graph(e);                          // kernels take DevState (S, max_quads, list32) by value
+}
 static int maybe_shrink_tile_cap(apj_engine* e) {
     if (e->cfg.tile_slots > 0) return APJ_OK;
     int need = 0;
@@ -261,7 +299,7 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
         st.mcap = st.gcap;
     }
     st.ntot = (long long)st.n_sys * st.cap;
-    st.S = cfg->max_neighbors > 0 ? (cfg->max_neighbors + 1) / 2 * 2 : 48;
+    st.S = cfg->max_neighbors > 0 ? (cfg->max_neighbors + 1) / 2 * 2 : 48;   // grown on demand (repair_list_overflow)
     if (st.S > apj_max_list_capacity()) { e->err = "apj_create: max_neighbors too large (<= 96)"; return bail(APJ_E_INVALID); }
     // lanes per particle: spread small systems over enough warps to hide latency (measured on B200)
     st.G = cfg->lanes_per_particle;
@@ -272,8 +310,7 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
 #endif
     st.tb = st.G == 1 ? APJ_TB_G1 : 128;
     st.ppb = st.tb / st.G;
-    st.max_rounds = (st.S / 2 + st.G - 1) / st.G;
-    st.max_quads = (st.max_rounds + 3) / 4;
+    set_list_capacity(st, st.S);
     // Engine constants exactly as the reference derives them (jamming.cpp:57, :112-115, :611)
     const double dt = cfg->dt > 0 ? cfg->dt : 0.1;
     const double rn = cfg->rn > 0 ? cfg->rn : 2.8;
@@ -397,6 +434,8 @@ extern "C" int apj_destroy(apj_engine* e) {
     for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void* p : e->allocs) cudaFree(p);
     if (e->pin_ctl) cudaFreeHost(e->pin_ctl);
+    if (e->pin_small) cudaFreeHost(e->pin_small);
+    if (e->stage_mem) cudaFree(e->stage_mem);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -435,9 +474,50 @@ static int run_chain_now(apj_engine* e) {
         if (int rc = pull_ctl(e)) return rc;
         int repaired = 0;
         if (int rc = repair_tile_overflow(e, &repaired)) return rc;
+        if (int rc = repair_list_overflow(e, &repaired)) return rc;
         if (!repaired) break;
     }
     return check_overflow(e);
+}
+
+// ---- state hand-over: staging planes + pack / unpack kernels (apj_state_io.cu) ---------------------
+static int ensure_stage(apj_engine* e, size_t n) {
+    if (!e->pin_small) APJ_CUDA(e, cudaMallocHost(&e->pin_small, 256));
+    n = std::max<size_t>(n, 1);
+    if (e->stage_n >= n) return APJ_OK;
+    if (e->stage_mem) { APJ_CUDA(e, cudaStreamSynchronize(e->stream)); cudaFree(e->stage_mem); e->stage_mem = nullptr; e->stage_n = 0; }
+    const size_t plane = (n * sizeof(double) + 255) / 256 * 256, iplane = (n * sizeof(int) + 255) / 256 * 256;
+    APJ_CUDA(e, cudaMalloc(&e->stage_mem, 14 * plane + 2 * iplane + 256));
+    char* p = static_cast<char*>(e->stage_mem);
+    for (int k = 0; k < 14; k++) e->stage.f[k] = reinterpret_cast<double*>(p + k * plane);
+    e->stage.box = reinterpret_cast<int*>(p + 14 * plane);
+    e->stage.ids = reinterpret_cast<int*>(p + 14 * plane + iplane);
+    e->stage.flag = reinterpret_cast<int*>(p + 14 * plane + 2 * iplane);
+    e->stage_n = n;
+    return APJ_OK;
+}
+static void state_planes(const apj_state* h, double* (&f)[14]) {
+    double* t[14] = {h->x, h->y, h->x_real, h->y_real, h->x0, h->y0, h->x_old, h->y_old, h->R, h->phi, h->cosp, h->sinp, h->vx, h->vy};
+    for (int k = 0; k < 14; k++) f[k] = t[k];
+}
+// H2D of every present field into the staging planes; returns the `present` mask of the pack kernel
+// (paired fields count only when both halves are given, as the documented defaults require)
+static int stage_in(apj_engine* e, const apj_state* h, size_t n, unsigned* present) {
+    double* f[14];
+    state_planes(h, f);
+    for (int k = 2; k < 14; k += 2) if (k != 8 && !(f[k] && f[k + 1])) f[k] = f[k + 1] = nullptr;
+    unsigned m = 0;
+    APJ_CUDA(e, cudaMemsetAsync(e->stage.flag, 0, sizeof(int), e->stream));
+    for (int k = 0; k < 14; k++)
+        if (f[k]) { m |= 1u << k; APJ_CUDA(e, cudaMemcpyAsync(e->stage.f[k], f[k], n * sizeof(double), cudaMemcpyHostToDevice, e->stream)); }
+    *present = m;
+    return APJ_OK;
+}
+static int stage_flag(apj_engine* e, int* flag) {
+    APJ_CUDA(e, cudaMemcpyAsync(e->pin_small, e->stage.flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    *flag = e->pin_small[0];
+    return APJ_OK;
 }
 
 extern "C" int apj_upload_state(apj_engine* e, const apj_state* h) {
@@ -446,98 +526,79 @@ extern "C" int apj_upload_state(apj_engine* e, const apj_state* h) {
     if (!h->phi && !(h->cosp && h->sinp)) return fail(e, APJ_E_INVALID, "apj_upload_state: phi or (cosp, sinp) required");
     if (e->st.slab) return fail(e, APJ_E_STATE, "apj_upload_state: slab handle, use apj_slab_upload");
     DevState& st = e->st;
-    const long long n = st.ntot;
+    const size_t n = (size_t)st.ntot;
     if (int rc = pull_ctl(e)) return rc;
-    std::vector<double2> xy(n), cs(n), rr(n), xr(n), x0(n), xo(n), v(n);
-    std::vector<double> phi(n);
-    std::vector<int> id(n), box(n);
+    if (int rc = ensure_stage(e, n)) return rc;
+    unsigned present = 0;
+    if (int rc = stage_in(e, h, n, &present)) return rc;
+    if (h->box) {
+        present |= 1u << 14;
+        APJ_CUDA(e, cudaMemcpyAsync(e->stage.box, h->box, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    }
+    // calculate_COM in index order (jamming.cpp:761-774) while the copies are in flight
+    const double* sx = (h->x_real && h->y_real) ? h->x_real : h->x;
+    const double* sy = (h->x_real && h->y_real) ? h->y_real : h->y;
     for (int s = 0; s < st.n_sys; s++) {
         SysCtl& c = e->hctl[s];
+        const double* px = sx + (size_t)s * st.N;
+        const double* py = sy + (size_t)s * st.N;
         double cx = 0.0, cy = 0.0;
-        for (int i = 0; i < st.N; i++) {
-            const long long g = (long long)s * st.N + i;
-            xy[g] = make_double2(h->x[g], h->y[g]);
-            phi[g] = h->phi ? h->phi[g] : std::atan2(h->sinp[g], h->cosp[g]);
-            cs[g].x = h->cosp ? h->cosp[g] : std::cos(h->phi[g]);   // jamming.cpp:332-333
-            cs[g].y = h->sinp ? h->sinp[g] : std::sin(h->phi[g]);
-            xr[g] = h->x_real ? make_double2(h->x_real[g], h->y_real[g]) : make_double2(h->x[g], h->y[g]);
-            x0[g] = h->x0 ? make_double2(h->x0[g], h->y0[g]) : xr[g];
-            xo[g] = h->x_old ? make_double2(h->x_old[g], h->y_old[g]) : make_double2(h->x[g], h->y[g]);
-            v[g] = h->vx ? make_double2(h->vx[g], h->vy[g]) : make_double2(0.0, 0.0);
-            rr[g] = make_double2(h->R[g], 1.0 / h->R[g]);            // Cell::R, Cell::Rinv (jamming.cpp:297-298)
-            id[g] = i;
-            int bx = h->box ? h->box[g] : -1;
-            if (bx >= 0 && bx < c.nbox) { const int qx = bx % c.b, qy = bx / c.b; bx = qy + qx * c.b; } else bx = -1;
-            box[g] = bx;
-            if (!(h->R[g] > 0.0)) return fail(e, APJ_E_INVALID, "apj_upload_state: radii must be positive");
-        }
-        for (int i = 0; i < st.N; i++) cx += xr[(long long)s * st.N + i].x;   // calculate_COM order (:761-774)
-        for (int i = 0; i < st.N; i++) cy += xr[(long long)s * st.N + i].y;
+        for (int i = 0; i < st.N; i++) { cx += px[i]; cy += py[i]; }
         c.COM[0] = cx / st.N; c.COM[1] = cy / st.N;
         c.COM_old[0] = c.COM0[0] = c.COM[0]; c.COM_old[1] = c.COM0[1] = c.COM[1];
         c.cur = 0; c.gen = 0; c.stale = 1; c.save_old = 0; c.ticket = 0; c.overflow = 0; c.list_max = 0;
         c.target = c.step;
     }
-    cudaStream_t q = e->stream;
-    APJ_CUDA(e, cudaMemcpyAsync(st.XY[0], xy.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.CS[0], cs.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.XR[0], xr.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.X0[0], x0.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.XO[0], xo.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.V[0], v.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.RR[0], rr.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.PHI[0], phi.data(), n * sizeof(double), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.ID[0], id.data(), n * sizeof(int), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.BOX[0], box.data(), n * sizeof(int), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemsetAsync(st.cell_count, 0, sizeof(int) * e->total_cells, q));
+    apj_launch_pack(st, e->stream, e->stage, present, (long long)n, 0);
+    e->launches++;
+    APJ_CUDA(e, cudaMemsetAsync(st.cell_count, 0, sizeof(int) * e->total_cells, e->stream));
+    int flag = 0;
+    if (int rc = stage_flag(e, &flag)) return rc;
+    if (flag & 1) return fail(e, APJ_E_INVALID, "apj_upload_state: radii must be positive");
     if (int rc = push_ctl(e)) return rc;
     e->have_state = true;
     return run_chain_now(e);   // assignCellsToGrid + buildVerletLists (start() :184-185)
+}
+
+// D2H of the wanted planes after apj_unpack_kernel filled them
+static int stage_out(apj_engine* e, const apj_state* h, size_t n, int by_id) {
+    double* f[14];
+    state_planes(h, f);
+    unsigned want = 0;
+    for (int k = 0; k < 14; k++) if (f[k]) want |= 1u << k;
+    if (h->box) want |= 1u << 14;
+    if (!want) return APJ_OK;
+    apj_launch_unpack(e->st, e->stream, e->stage, want, by_id);
+    e->launches++;
+    for (int k = 0; k < 14; k++)
+        if (f[k]) APJ_CUDA(e, cudaMemcpyAsync(f[k], e->stage.f[k], n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (h->box) APJ_CUDA(e, cudaMemcpyAsync(h->box, e->stage.box, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    return APJ_OK;
 }
 
 extern "C" int apj_download_state(apj_engine* e, apj_state* h) {
     if (!e || !h) return APJ_E_INVALID;
     if (!e->have_state) return fail(e, APJ_E_STATE, "apj_download_state: no state uploaded");
     if (e->st.slab) return fail(e, APJ_E_STATE, "apj_download_state: slab handle, use apj_slab_download");
-    DevState& st = e->st;
-    const long long n = st.ntot;
-    if (int rc = pull_ctl(e)) return rc;
-    // all systems share parity only if they committed the same number of steps; handle per system
-    std::vector<double2> xy(n), cs(n), rr(n), xr(n), x0(n), xo(n), v(n);
-    std::vector<double> phi(n);
-    std::vector<int> id(n), box(n);
-    cudaStream_t q = e->stream;
-    for (int s = 0; s < st.n_sys; s++) {
-        const SysCtl& c = e->hctl[s];
-        const long long o = (long long)s * st.N;
-        const size_t N = st.N;
-        APJ_CUDA(e, cudaMemcpyAsync(xy.data() + o, st.XY[c.cur] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
-        APJ_CUDA(e, cudaMemcpyAsync(cs.data() + o, st.CS[c.cur] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
-        APJ_CUDA(e, cudaMemcpyAsync(xr.data() + o, st.XR[c.cur] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
-        APJ_CUDA(e, cudaMemcpyAsync(x0.data() + o, st.X0[c.gen] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
-        APJ_CUDA(e, cudaMemcpyAsync(xo.data() + o, st.XO[c.gen] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
-        APJ_CUDA(e, cudaMemcpyAsync(v.data() + o, st.V[c.gen] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
-        APJ_CUDA(e, cudaMemcpyAsync(rr.data() + o, st.RR[c.gen] + o, N * sizeof(double2), cudaMemcpyDeviceToHost, q));
-        APJ_CUDA(e, cudaMemcpyAsync(phi.data() + o, st.PHI[c.gen] + o, N * sizeof(double), cudaMemcpyDeviceToHost, q));
-        APJ_CUDA(e, cudaMemcpyAsync(id.data() + o, st.ID[c.gen] + o, N * sizeof(int), cudaMemcpyDeviceToHost, q));
-        APJ_CUDA(e, cudaMemcpyAsync(box.data() + o, st.BOX[c.gen] + o, N * sizeof(int), cudaMemcpyDeviceToHost, q));
-    }
-    APJ_CUDA(e, cudaStreamSynchronize(q));
-    for (int s = 0; s < st.n_sys; s++) {
-        const SysCtl& c = e->hctl[s];
-        for (int k = 0; k < st.N; k++) {
-            const long long g = (long long)s * st.N + k;
-            const long long d = (long long)s * st.N + id[g];
-            if (h->x) h->x[d] = xy[g].x;           if (h->y) h->y[d] = xy[g].y;
-            if (h->cosp) h->cosp[d] = cs[g].x;     if (h->sinp) h->sinp[d] = cs[g].y;
-            if (h->x_real) h->x_real[d] = xr[g].x; if (h->y_real) h->y_real[d] = xr[g].y;
-            if (h->x0) h->x0[d] = x0[g].x;         if (h->y0) h->y0[d] = x0[g].y;
-            if (h->x_old) h->x_old[d] = xo[g].x;   if (h->y_old) h->y_old[d] = xo[g].y;
-            if (h->vx) h->vx[d] = v[g].x;          if (h->vy) h->vy[d] = v[g].y;
-            if (h->R) h->R[d] = rr[g].x;              if (h->phi) h->phi[d] = phi[g];
-            if (h->box) { const int bi = box[g]; h->box[d] = bi < 0 ? -1 : (bi / c.b) + (bi % c.b) * c.b; }
-        }
-    }
+    const size_t n = (size_t)e->st.ntot;
+    if (int rc = ensure_stage(e, n)) return rc;
+    if (int rc = stage_out(e, h, n, 1)) return rc;       // scatter by id: original particle order
+    return pull_ctl(e);                                   // synchronises the stream; refreshes hctl (checkpoint writer)
+}
+
+// 64-bit fingerprint of {id, x, y, cos, sin} summed over the owned particles: independent of particle order
+// and of the slab decomposition (ranks add their shares modulo 2^64).
+extern "C" int apj_state_checksum(apj_engine* e, uint64_t* out) {
+    if (!e || !out) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_state_checksum: no state uploaded");
+    if (int rc = ensure_stage(e, 1)) return rc;
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(e->obs.d_hist);
+    APJ_CUDA(e, cudaMemsetAsync(d, 0, sizeof(unsigned long long), e->stream));
+    apj_launch_checksum(e->st, e->stream, d);
+    e->launches++;
+    APJ_CUDA(e, cudaMemcpyAsync(e->pin_small, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(out, e->pin_small, sizeof(uint64_t));
     return APJ_OK;
 }
 
@@ -706,12 +767,21 @@ extern "C" int apj_step(apj_engine* e, int64_t n_steps) {
     e->launches++;
     long long remaining = n_steps;
     for (int guard = 0; guard < 1 << 20; guard++) {
-        const long long groups = (remaining + e->m - 1) / e->m + (guard ? 0 : 1);
-        for (long long k = 0; k < groups; k++)
+        // whole groups through the graph, the remainder as direct launches: no launch is issued that cannot
+        // commit a step unless a rebuild fires (the speculative step is dropped and the rest of ITS group idles)
+        const long long full = remaining / e->m, rem = remaining % e->m;
+        for (long long k = 0; k < full; k++)
             if (int rc = launch_group(e)) return rc;
+        if (rem || !full) {
+            ApjLaunch l = launcher(e, true);
+            for (long long k = 0; k < rem; k++) apj_launch_step(st, l, nullptr, 0);
+            apj_launch_rebuild_chain(st, l, e->max_nbox, e->max_b);
+            APJ_CUDA(e, cudaGetLastError());
+        }
         if (int rc = pull_ctl(e)) return rc;
         int repaired = 0;
         if (int rc = repair_tile_overflow(e, &repaired)) return rc;
+        if (int rc = repair_list_overflow(e, &repaired)) return rc;
         if (int rc = check_overflow(e)) return rc;
         if (all_done(e, &remaining)) return APJ_OK;
     }
@@ -733,6 +803,7 @@ extern "C" int apj_step_injected(apj_engine* e, const double* noise) {
         if (int rc = pull_ctl(e)) return rc;
         int repaired = 0;
         if (int rc = repair_tile_overflow(e, &repaired)) return rc;
+        if (int rc = repair_list_overflow(e, &repaired)) return rc;
         if (int rc = check_overflow(e)) return rc;
         long long remaining;
         if (all_done(e, &remaining)) return APJ_OK;
@@ -844,34 +915,54 @@ extern "C" int apj_get_pair_list(apj_engine* e, int32_t s, int64_t* offsets, int
     APJ_CUDA(e, cudaMemcpyAsync(tiles.data(), st.tiles + (size_t)s * st.maxblk, c.nblk * sizeof(TileDesc), cudaMemcpyDeviceToHost, e->stream));
     APJ_CUDA(e, cudaMemcpyAsync(lst.data(), st.list32 + (size_t)s * st.maxblk * words_per_blk, lst.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
     APJ_CUDA(e, cudaStreamSynchronize(e->stream));
-    // decode tile slots -> particle index -> id; keep partners with larger id, ascending
-    std::vector<std::vector<int>> half(N);
+    // decode tile slots -> particle index -> id; keep partners with larger id, ascending. Two passes over
+    // the lists (count, fill) into CSR rows by id, so the 16M-particle box needs no per-particle containers.
+    std::vector<int64_t> row(N + 1, 0);
+    std::vector<int> buf;
     size_t covered = 0;
-    for (int blk = 0; blk < c.nblk; blk++) {
-        const TileDesc& d = tiles[blk];
-        for (int t = 0; t < d.n; t++, covered++) {
-            const long long g = d.g0 + t - o;
-            if (g < 0 || g >= (long long)N) return fail(e, APJ_E_STATE, "apj_get_pair_list: tile outside its system");
-            for (int k = 0; k < cnt[g]; k++) {
-                const int wi = k >> 1, sub = wi % st.G, kk = wi / st.G;
-                const unsigned w = lst[blk * words_per_blk + ((size_t)(kk >> 2) * st.tb + (size_t)t * st.G + sub) * 4 + (kk & 3)];
-                int slot = (int)(((k & 1) ? (w >> 16) : (w & 0xffffu)) >> 4) - 1;   // entries are (1-based slot) * 16
-                long long j = -1;
-                for (int p = 0; p < (d.info & 0xff); p++) {
-                    if (slot < d.plen[p]) { j = (long long)d.pstart[p] + slot - o; break; }
-                    slot -= d.plen[p];
+    for (int pass = 0; pass < 2; pass++) {
+        covered = 0;
+        for (int blk = 0; blk < c.nblk; blk++) {
+            const TileDesc& d = tiles[blk];
+            for (int t = 0; t < d.n; t++, covered++) {
+                const long long g = d.g0 + t - o;
+                if (g < 0 || g >= (long long)N) return fail(e, APJ_E_STATE, "apj_get_pair_list: tile outside its system");
+                for (int k = 0; k < cnt[g]; k++) {
+                    const int wi = k >> 1, sub = wi % st.G, kk = wi / st.G;
+                    const unsigned w = lst[blk * words_per_blk + ((size_t)(kk >> 2) * st.tb + (size_t)t * st.G + sub) * 4 + (kk & 3)];
+                    int slot = (int)(((k & 1) ? (w >> 16) : (w & 0xffffu)) >> 4) - 1;   // entries are (1-based slot) * 16
+                    long long j = -1;
+                    for (int p = 0; p < (d.info & 0xff); p++) {
+                        if (slot < d.plen[p]) { j = (long long)d.pstart[p] + slot - o; break; }
+                        slot -= d.plen[p];
+                    }
+                    if (j < 0 || j >= (long long)N) return fail(e, APJ_E_STATE, "apj_get_pair_list: list entry outside its tile");
+                    if (id[j] > id[g]) {
+                        if (pass == 0) row[id[g] + 1]++;
+                        else buf[row[id[g]]++] = id[j];
+                    }
                 }
-                if (j < 0 || j >= (long long)N) return fail(e, APJ_E_STATE, "apj_get_pair_list: list entry outside its tile");
-                if (id[j] > id[g]) half[id[g]].push_back(id[j]);
             }
         }
+        if (covered != N) return fail(e, APJ_E_STATE, "apj_get_pair_list: work blocks do not cover the system");
+        if (pass == 0) {
+            for (size_t i = 0; i < N; i++) row[i + 1] += row[i];
+            if (!idx || cap < row[N]) {              // size query (or a buffer that cannot hold the pairs)
+                if (offsets) for (size_t i = 0; i <= N; i++) offsets[i] = row[i];
+                *total = row[N];
+                return APJ_OK;
+            }
+            buf.resize((size_t)row[N]);
+        }
     }
-    if (covered != N) return fail(e, APJ_E_STATE, "apj_get_pair_list: work blocks do not cover the system");
+    // the fill advanced row[i] to the end of row i: row i is [row[i-1], row[i])
     int64_t tot = 0;
     for (size_t i = 0; i < N; i++) {
-        std::sort(half[i].begin(), half[i].end());
-        if (offsets) offsets[i] = tot;
-        for (int j : half[i]) { if (idx && tot < cap) idx[tot] = j; tot++; }
+        const int64_t r0 = i ? row[i - 1] : 0, r1 = row[i];
+        std::sort(buf.begin() + r0, buf.begin() + r1);
+        if (offsets) offsets[i] = r0;
+        for (int64_t q = r0; q < r1; q++) idx[q] = buf[q];
+        tot = r1;
     }
     if (offsets) offsets[N] = tot;
     *total = tot;
@@ -961,7 +1052,12 @@ extern "C" int apj_time_step_kernel(apj_engine* e, int64_t n, float* mean_ms, in
     DevState& st = e->st;
     if (int rc = pull_ctl(e)) return rc;
     const long long step0 = e->hctl[0].step;
-    std::vector<cudaEvent_t> ev(2 * n);
+    struct Events {   // destroyed on every return path
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (auto x : v) if (x) cudaEventDestroy(x); }
+    } evs;
+    evs.v.assign(2 * n, nullptr);
+    std::vector<cudaEvent_t>& ev = evs.v;
     for (auto& x : ev) APJ_CUDA(e, cudaEventCreate(&x));
     ApjLaunch l = launcher(e, true);
     // one target for the whole series (as apj_step does): only the very last step takes the
@@ -977,7 +1073,6 @@ extern "C" int apj_time_step_kernel(apj_engine* e, int64_t n, float* mean_ms, in
     APJ_CUDA(e, cudaStreamSynchronize(e->stream));
     double tot = 0;
     for (int64_t k = 0; k < n; k++) { float ms = 0; APJ_CUDA(e, cudaEventElapsedTime(&ms, ev[2 * k], ev[2 * k + 1])); tot += ms; }
-    for (auto& x : ev) cudaEventDestroy(x);
     *mean_ms = (float)(tot / n);
     if (int rc = pull_ctl(e)) return rc;
     if (committed) *committed = e->hctl[0].step - step0;
@@ -1071,38 +1166,23 @@ extern "C" int apj_slab_upload(apj_engine* e, const apj_state* h, const int32_t*
     if (n_local > st.cap) return fail(e, APJ_E_OVERFLOW, "apj_slab_upload: more particles than this rank's capacity");
     if (int rc = pull_ctl(e)) return rc;
     const size_t n = (size_t)n_local;
-    std::vector<double2> xy(n), cs(n), rr(n), xr(n), x0(n), xo(n), v(n);
-    std::vector<double> phi(n);
-    std::vector<int> id(n), box(n, -1);
-    for (size_t g = 0; g < n; g++) {
-        xy[g] = make_double2(h->x[g], h->y[g]);
-        phi[g] = h->phi ? h->phi[g] : std::atan2(h->sinp[g], h->cosp[g]);
-        cs[g].x = h->cosp ? h->cosp[g] : std::cos(h->phi[g]);   // jamming.cpp:332-333
-        cs[g].y = h->sinp ? h->sinp[g] : std::sin(h->phi[g]);
-        xr[g] = h->x_real ? make_double2(h->x_real[g], h->y_real[g]) : xy[g];
-        x0[g] = h->x0 ? make_double2(h->x0[g], h->y0[g]) : xr[g];
-        xo[g] = h->x_old ? make_double2(h->x_old[g], h->y_old[g]) : xy[g];
-        v[g] = h->vx ? make_double2(h->vx[g], h->vy[g]) : make_double2(0.0, 0.0);
-        if (!(h->R[g] > 0.0)) return fail(e, APJ_E_INVALID, "apj_slab_upload: radii must be positive");
-        rr[g] = make_double2(h->R[g], 1.0 / h->R[g]);
-        if (ids[g] < 0 || ids[g] >= st.N) return fail(e, APJ_E_INVALID, "apj_slab_upload: particle id outside [0, N)");
-        id[g] = ids[g];
+    if (int rc = ensure_stage(e, (size_t)st.cap)) return rc;
+    unsigned present = 0;
+    if (n > 0) {
+        if (int rc = stage_in(e, h, n, &present)) return rc;
+        APJ_CUDA(e, cudaMemcpyAsync(e->stage.ids, ids, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        apj_launch_pack(st, e->stream, e->stage, present, (long long)n, 1);
+        e->launches++;
+        int flag = 0;
+        if (int rc = stage_flag(e, &flag)) return rc;
+        // NOTE: the other ranks are already inside the collective rebuild; they report the missing peer after the timeout
+        if (flag & 1) return fail(e, APJ_E_INVALID, "apj_slab_upload: radii must be positive");
+        if (flag & 2) return fail(e, APJ_E_INVALID, "apj_slab_upload: particle id outside [0, N)");
     }
     SysCtl& c = e->hctl[0];
     c.cur = 0; c.gen = 0; c.stale = 1; c.save_old = 0; c.ticket = 0; c.overflow = 0; c.list_max = 0;
     c.target = c.step; c.n_own = (int)n_local; c.p0 = 0;
-    cudaStream_t q = e->stream;
-    APJ_CUDA(e, cudaMemcpyAsync(st.XY[0], xy.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.CS[0], cs.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.XR[0], xr.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.X0[0], x0.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.XO[0], xo.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.V[0], v.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.RR[0], rr.data(), n * sizeof(double2), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.PHI[0], phi.data(), n * sizeof(double), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.ID[0], id.data(), n * sizeof(int), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemcpyAsync(st.BOX[0], box.data(), n * sizeof(int), cudaMemcpyHostToDevice, q));
-    APJ_CUDA(e, cudaMemsetAsync(st.cell_count, 0, sizeof(int) * e->total_cells, q));
+    APJ_CUDA(e, cudaMemsetAsync(st.cell_count, 0, sizeof(int) * e->total_cells, e->stream));
     if (int rc = push_ctl(e)) return rc;
     e->have_state = true;
     return run_chain_now(e);   // collective: migration of misplaced particles, ghost columns, lists
@@ -1117,31 +1197,11 @@ extern "C" int apj_slab_download(apj_engine* e, apj_state* h, int32_t* ids, int6
     const size_t n = (size_t)c.n_own;
     *n_local = (int64_t)n;
     if (!ids || cap < (int64_t)n) return cap < (int64_t)n && ids ? fail(e, APJ_E_INVALID, "apj_slab_download: buffers too small") : APJ_OK;
-    std::vector<double2> xy(n), cs(n), rr(n), xr(n), x0(n), xo(n), v(n);
-    std::vector<double> phi(n);
-    std::vector<int> box(n);
-    cudaStream_t q = e->stream;
-    APJ_CUDA(e, cudaMemcpyAsync(xy.data(), st.XY[c.cur], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
-    APJ_CUDA(e, cudaMemcpyAsync(cs.data(), st.CS[c.cur], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
-    APJ_CUDA(e, cudaMemcpyAsync(xr.data(), st.XR[c.cur], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
-    APJ_CUDA(e, cudaMemcpyAsync(x0.data(), st.X0[c.gen], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
-    APJ_CUDA(e, cudaMemcpyAsync(xo.data(), st.XO[c.gen], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
-    APJ_CUDA(e, cudaMemcpyAsync(v.data(), st.V[c.gen], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
-    APJ_CUDA(e, cudaMemcpyAsync(rr.data(), st.RR[c.gen], n * sizeof(double2), cudaMemcpyDeviceToHost, q));
-    APJ_CUDA(e, cudaMemcpyAsync(phi.data(), st.PHI[c.gen], n * sizeof(double), cudaMemcpyDeviceToHost, q));
-    APJ_CUDA(e, cudaMemcpyAsync(ids, st.ID[c.gen], n * sizeof(int), cudaMemcpyDeviceToHost, q));
-    APJ_CUDA(e, cudaMemcpyAsync(box.data(), st.BOX[c.gen], n * sizeof(int), cudaMemcpyDeviceToHost, q));
-    APJ_CUDA(e, cudaStreamSynchronize(q));
-    for (size_t g = 0; g < n; g++) {
-        if (h->x) h->x[g] = xy[g].x;           if (h->y) h->y[g] = xy[g].y;
-        if (h->cosp) h->cosp[g] = cs[g].x;     if (h->sinp) h->sinp[g] = cs[g].y;
-        if (h->x_real) h->x_real[g] = xr[g].x; if (h->y_real) h->y_real[g] = xr[g].y;
-        if (h->x0) h->x0[g] = x0[g].x;         if (h->y0) h->y0[g] = x0[g].y;
-        if (h->x_old) h->x_old[g] = xo[g].x;   if (h->y_old) h->y_old[g] = xo[g].y;
-        if (h->vx) h->vx[g] = v[g].x;          if (h->vy) h->vy[g] = v[g].y;
-        if (h->R) h->R[g] = rr[g].x;           if (h->phi) h->phi[g] = phi[g];
-        if (h->box) { const int bi = box[g]; h->box[g] = bi < 0 ? -1 : (bi / c.b + c.col0) + (bi % c.b) * c.b; }   // reference numbering i + j*b
-    }
+    if (n == 0) return APJ_OK;
+    if (int rc = ensure_stage(e, (size_t)st.cap)) return rc;
+    if (int rc = stage_out(e, h, n, 0)) return rc;       // device (cell) order; the ids say who is who
+    APJ_CUDA(e, cudaMemcpyAsync(ids, st.ID[c.gen], n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
     return APJ_OK;
 }
 

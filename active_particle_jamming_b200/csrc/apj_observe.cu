@@ -268,6 +268,11 @@ int apj_obs_spatial(ApjObsScratch* o, const DevState& st, cudaStream_t s, long l
     if (need > o->corr_cap) {
         void* p = nullptr;
         if (cudaMalloc(&p, need * sizeof(double)) != cudaSuccess) return APJ_E_CUDA_OBS;
+        if (o->d_corr) {   // replace the smaller buffer (work queued on it has to drain first)
+            cudaStreamSynchronize(s);
+            allocs.erase(std::remove(allocs.begin(), allocs.end(), (void*)o->d_corr), allocs.end());
+            cudaFree(o->d_corr);
+        }
         allocs.push_back(p);
         o->d_corr = (double*)p; o->corr_cap = need;
     }

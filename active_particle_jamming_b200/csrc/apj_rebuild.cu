@@ -624,6 +624,9 @@ __global__ void apj_finish_rebuild_kernel(const DevState st) {
     if (!ctl->stale) return;
     if (ctl->overflow & 2) return;   // tile larger than the launched shared-memory capacity: nothing was
                                      // committed, the system stays stale until the host re-launches bigger
+    if ((ctl->overflow & 1) && !st.slab) return;   // a list did not fit: same -- no step may run on truncated lists;
+                                     // the host grows the list storage and runs the chain again (slab ranks move in
+                                     // lockstep and cannot stall alone: there the host reports the overflow)
     ctl->cur ^= 1;
     ctl->gen ^= 1;
     if (ctl->save_old) {   // newSkinList fired (jamming.cpp:611-615): resetCounter++, saveOldPositions

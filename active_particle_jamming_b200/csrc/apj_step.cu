@@ -367,7 +367,8 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
             // Both forms are within ~1e-15 of the exact value (measured 1.2e-15 apart over 1.2e7 samples),
             // far inside the 1e-12 gate. The reference's wrap uses truncated constants: when theta + eta
             // leaves [-PI, PI) it shifts phi by PI2 = 6.28318531, i.e. rotates (cos, sin) by PI2 - 2 pi.
-            // Whether it wraps follows from the signs: for eta > 0 (theta >= 0 required) phi >= PI iff
+            // Whether it wraps follows from the signs (theta = atan2(ay, ax) carries the sign BIT of ay, so
+            // ay = -0.0 with ax < 0 is theta = -pi): for eta > 0 (theta >= 0 required) phi >= PI iff
             // sin(phi) < 0, or cos(phi) < 0 and sin(phi) <= sin(PI); mirrored for eta < 0.
             double sn_n, cn_n;
             sincos(nz, &sn_n, &cn_n);
@@ -377,9 +378,9 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
             sn = s0 * cn_n + c0 * sn_n;
             constexpr double SIN_PI = 3.5897930298416118e-09;    // sin(3.14159265) evaluated on the double constant
             constexpr double DPI2 = 2.8204138795420667e-09;      // 6.28318531 (as a double) - 2 pi
-            if (nz > 0.0 && ay >= 0.0 && (sn < 0.0 || (cs < 0.0 && sn <= SIN_PI))) {
+            if (nz > 0.0 && !signbit(ay) && (sn < 0.0 || (cs < 0.0 && sn <= SIN_PI))) {
                 const double c = cs; cs = c + sn * DPI2; sn = sn - c * DPI2;      // phi -= PI2
-            } else if (nz < 0.0 && ay < 0.0 && (sn > 0.0 || (cs < 0.0 && sn > -SIN_PI))) {
+            } else if (nz < 0.0 && signbit(ay) && (sn > 0.0 || (cs < 0.0 && sn > -SIN_PI))) {
                 const double c = cs; cs = c - sn * DPI2; sn = sn + c * DPI2;      // phi += PI2
             }
         }

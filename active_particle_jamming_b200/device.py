@@ -41,7 +41,7 @@ class _State(C.Structure):
 
 
 EXPORTS = ["apj_version", "apj_last_error", "apj_create", "apj_destroy", "apj_set_activity", "apj_set_ramp",
-           "apj_upload_state", "apj_download_state", "apj_set_com", "apj_get_com", "apj_mark_origin",
+           "apj_upload_state", "apj_download_state", "apj_state_checksum", "apj_set_com", "apj_get_com", "apj_mark_origin",
            "apj_skip_self_term_once", "apj_step", "apj_step_injected", "apj_force_rebuild", "apj_sync", "apj_save_checkpoint", "apj_load_checkpoint",
            "apj_get_counters", "apj_get_sweep_stats", "apj_set_sweep_truncation", "apj_get_tuning", "apj_set_reset_counter", "apj_get_geometry", "apj_get_pair_list", "apj_get_cell_lists", "apj_list_stats",
            "apj_order_orientation", "apj_msd", "apj_fluct_area", "apj_spatial_correlations", "apj_vel_hist",
@@ -71,6 +71,7 @@ def load_library():
     L.apj_set_ramp.argtypes = [C.c_void_p, C.c_int64]
     L.apj_upload_state.argtypes = [C.c_void_p, C.POINTER(_State)]
     L.apj_download_state.argtypes = [C.c_void_p, C.POINTER(_State)]
+    L.apj_state_checksum.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.apj_set_com.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _dp]
     L.apj_get_com.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _dp]
     L.apj_mark_origin.argtypes = [C.c_void_p]
@@ -184,19 +185,31 @@ class DeviceEngine:
             keep.append(a)
         self._chk(self.lib.apj_upload_state(self.h, C.byref(st)))
 
-    def download(self, fields=None):
+    def download(self, fields=None, out=None):
+        """{field: array[n_systems * n]} in original particle order. `out` may hold preallocated (e.g.
+        page-locked) arrays to receive the fields."""
         fields = list(fields) if fields is not None else STATE_FIELDS + ["box"]
         st = _State()
-        out = {}
+        out = dict(out) if out is not None else {}
         for k in fields:
+            want = np.int32 if k == "box" else np.float64
+            a = out.get(k)
+            if a is None:
+                a = out[k] = np.empty(self.ntot, dtype=want)
+            if a.dtype != want or a.size != self.ntot or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("download: out[%r] must be a contiguous %s array of %d values" % (k, want.__name__, self.ntot))
             if k == "box":
-                out[k] = np.zeros(self.ntot, dtype=np.int32)
-                st.box = _p(out[k], _ip)
+                st.box = _p(a, _ip)
             else:
-                out[k] = np.zeros(self.ntot)
-                setattr(st, k, _p(out[k]))
+                setattr(st, k, _p(a))
         self._chk(self.lib.apj_download_state(self.h, C.byref(st)))
-        return out
+        return {k: out[k] for k in fields}
+
+    def checksum(self):
+        """64-bit fingerprint of {id, x, y, cos, sin} over the particles this handle owns (apj_state_checksum)."""
+        v = C.c_uint64(0)
+        self._chk(self.lib.apj_state_checksum(self.h, C.byref(v)))
+        return int(v.value)
 
     def set_com(self, system=0, com=None, com0=None, com_old=None):
         a = [None if v is None else _f64(v, 2) for v in (com, com0, com_old)]

@@ -31,7 +31,7 @@ struct ApjBatch
     void check(int rc, const char* what) const {
         if (rc == APJ_OK) return;
         fprintf(stdout, "%s failed (%d): %s\n", what, rc, apj_last_error(dev));
-        exit(720);
+        exit(120);
     }
     void touch() { version++; }
 

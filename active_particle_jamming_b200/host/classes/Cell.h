@@ -79,7 +79,7 @@ inline void Cell::update(double&)
 {
     fprintf(stderr, "Cell::update: the per-particle update runs on the GPU inside apj_step(); "
                     "this build has no CPU path. Call Engine::calculate_next_positions().\n");
-    exit(718);
+    exit(118);
 }
 
 // Host-side setup helpers used by Engine::initCells, same single-wrap semantics and truncated

@@ -45,7 +45,7 @@ struct Correlations
 
 private:
     void need_device(const char* who) const {
-        if (!batch || !batch->dev) { fprintf(stderr, "Correlations::%s: no device engine bound (this build has no CPU path)\n", who); exit(717); }
+        if (!batch || !batch->dev) { fprintf(stderr, "Correlations::%s: no device engine bound (this build has no CPU path)\n", who); exit(117); }
     }
 };
 

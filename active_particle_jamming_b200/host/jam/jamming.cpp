@@ -161,7 +161,7 @@ void Engine::check(int rc, const char* what)
 {
     if (rc == APJ_OK) return;
     cout << what << " failed (" << rc << "): " << apj_last_error(dev) << endl;
-    exit(720);
+    exit(120);
 }
 
 Engine::Engine(string dir, string ID, long int n, long int steps, double l_s, double l_n, double rho)
@@ -282,10 +282,12 @@ ApjBatch* Engine::attach_batch(vector<Engine*>& runs)
     cfg.device = d ? atoi(d) : 0;
     cfg.dt = runs[0]->dt; cfg.rn = runs[0]->rn; cfg.rs_factor = runs[0]->rs/runs[0]->rn;
     cfg.seed = g_seed;
+    const char* mn = getenv("APJ_MAX_NEIGHBORS");      // initial Verlet-list capacity; the library grows it on demand
+    cfg.max_neighbors = mn ? atoi(mn) : 0;
     vector<double> Ls(S), CF(S), CT(S);
     for (int s = 0; s < S; s++) { Ls[s] = runs[s]->L; CF[s] = runs[s]->CFself; CT[s] = runs[s]->CTnoise; }
     int rc = apj_create(&cfg, Ls.data(), &b->dev);
-    if (rc != APJ_OK) { cout << "apj_create failed (" << rc << "): " << apj_last_error(NULL) << endl; exit(720); }
+    if (rc != APJ_OK) { cout << "apj_create failed (" << rc << "): " << apj_last_error(NULL) << endl; exit(120); }
     b->check(apj_set_activity(b->dev, CF.data(), CT.data()), "apj_set_activity");
 
     const size_t T = (size_t)S*N;

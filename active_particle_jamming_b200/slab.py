@@ -136,22 +136,27 @@ class SlabRank(DeviceEngine):
             keep.append(a)
         self._chk(self.lib.apj_slab_upload(self.h, C.byref(st), _p(ids, _ip), ids.size))
 
-    def download_local(self, fields=None):
+    def download_local(self, fields=None, out=None, ids_out=None):
+        """(ids, {field: values}) of the owned particles in device order. `out` / `ids_out` may hold
+        preallocated (e.g. page-locked) arrays of at least n_own entries."""
         fields = list(fields) if fields is not None else STATE_FIELDS + ["box"]
         n = C.c_int64(0)
         st = _State()
         self._chk(self.lib.apj_slab_download(self.h, C.byref(st), None, 0, C.byref(n)))
-        ids = np.zeros(max(n.value, 1), dtype=np.int32)
-        out = {}
+        m = max(n.value, 1)
+        ids = ids_out if ids_out is not None and ids_out.size >= m and ids_out.dtype == np.int32 else np.empty(m, dtype=np.int32)
+        out = dict(out) if out is not None else {}
         for k in fields:
+            want = np.int32 if k == "box" else np.float64
+            a = out.get(k)
+            if a is None or a.size < m or a.dtype != want or not a.flags["C_CONTIGUOUS"]:
+                a = out[k] = np.empty(m, dtype=want)
             if k == "box":
-                out[k] = np.zeros(max(n.value, 1), dtype=np.int32)
-                st.box = _p(out[k], _ip)
+                st.box = _p(a, _ip)
             else:
-                out[k] = np.zeros(max(n.value, 1))
-                setattr(st, k, _p(out[k]))
+                setattr(st, k, _p(a))
         self._chk(self.lib.apj_slab_download(self.h, C.byref(st), _p(ids, _ip), ids.size, C.byref(n)))
-        return ids[:n.value], {k: v[:n.value] for k, v in out.items()}
+        return ids[:n.value], {k: out[k][:n.value] for k in fields}
 
     def pairs(self):
         tot = C.c_int64(0)
@@ -235,6 +240,13 @@ class _SlabFront:
 
     def n_own(self):
         return [r.info()["n_own"] for r in self.local]
+
+    def checksum(self):
+        """Fingerprint of the whole box: the ranks' shares add modulo 2^64 (equals DeviceEngine.checksum of
+        the same state on one GPU)."""
+        mine = sum(r.checksum() for r in self.local) & 0xffffffffffffffff
+        parts = self._allsum(np.array([float(mine >> 43), float((mine >> 22) & 0x1fffff), float(mine & 0x3fffff)]))
+        return (int(parts[0]) * (1 << 43) + int(parts[1]) * (1 << 22) + int(parts[2])) & 0xffffffffffffffff
 
     # observables: additive shares
     def order_orientation(self):

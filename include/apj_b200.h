@@ -92,6 +92,14 @@ int apj_set_ramp(apj_engine* e, int64_t tthermalize);
  * buildVerletLists, start() :184-185) WITHOUT touching x_old. */
 int apj_upload_state(apj_engine* e, const apj_state* host);
 int apj_download_state(apj_engine* e, apj_state* host);
+/* Both copy the caller's arrays field by field (cudaMemcpyAsync on the handle's stream: page-locked caller
+ * buffers move at PCIe speed, pageable ones work but are staged by the driver) through staging planes in
+ * HBM; the AoS <-> SoA interleave, Rinv, cos/sin(phi), box renumbering and the by-id scatter run in kernels.
+ *
+ * 64-bit fingerprint of the current state: sum over particles of a hash of (system, id, bits of x, y, cos,
+ * sin). It does not depend on the particle order in memory nor, on slab handles, on the decomposition: the
+ * value of a slab handle is this rank's share, shares add modulo 2^64 to the value of the periodic handle. */
+int apj_state_checksum(apj_engine* e, uint64_t* out);
 /* COM / COM0 / COM_old of one system (jamming.cpp:89-91); NULL pointers are skipped. */
 int apj_set_com(apj_engine* e, int32_t system, const double* com, const double* com0, const double* com_old);
 int apj_get_com(apj_engine* e, int32_t system, double* com, double* com0, double* com_old);

@@ -210,17 +210,141 @@ def test_error_paths():
     with pytest.raises(ApjError):
         e.upload(x=np.zeros(1024), y=np.zeros(1024))                        # R, phi missing
     e.close()
-    # list capacity: all particles in one spot -> more neighbours than max_neighbors
+    # list capacity beyond what the layout holds (96): everything in one spot
     R, L, x, y, phi = random_system(1024, 0.9, 3)
     e = DeviceEngine(1024, L, max_neighbors=8)
     with pytest.raises(ApjError) as ei:
-        e.upload(x=x, y=y, R=R, phi=phi)
+        e.upload(x=x / 50, y=y / 50, R=R, phi=phi)
     assert ei.value.code == -3 and "max_neighbors" in str(ei.value)
+    e.close()
+    # non-positive radius: found by the pack kernel
+    e = DeviceEngine(1024, L)
+    Rb = R.copy(); Rb[17] = 0.0
+    with pytest.raises(ApjError) as ei:
+        e.upload(x=x, y=y, R=Rb, phi=phi)
+    assert ei.value.code == -1 and "radii" in str(ei.value)
     e.close()
     with device_from_state(relaxed_oracle(1024, 0.9, 1)[0].state()) as e:
         with pytest.raises(ApjError) as ei:
             e.spatial_correlations(19.0)
         assert ei.value.code == -1
+
+
+def test_list_capacity_grows_instead_of_truncating():
+    """A list longer than max_neighbors must never be truncated: the system stays stale, the
+    library re-allocates the list storage and re-runs the chain -- at upload and in the middle of apj_step
+    (a clustering run) -- and the pair set / trajectory equal those of a handle created large enough."""
+    N, rho = 4096, 0.9
+    o, _ = relaxed_oracle(N, rho, seed=21, l_s=0.5, l_n=0.3, presteps=20)     # 20 steps from a random start: lists up to ~40
+    s = o.state()
+    o.assign(); o.build()
+    ref_pairs = o.pair_set()
+    o.close()
+    with device_from_state(s, seed=5, max_neighbors=8) as small, device_from_state(s, seed=5, max_neighbors=96) as big:
+        assert small.counters()["overflow"] == 0
+        assert np.array_equal(small.pair_set(), ref_pairs) and np.array_equal(big.pair_set(), ref_pairs)
+        small.step(200); big.step(200)
+        a, b = small.download(), big.download()
+        for f in ("x", "y", "cosp", "sinp", "x_real", "x_old"):
+            assert np.array_equal(a[f], b[f]), f
+        assert small.counters()["resetCounter"] == big.counters()["resetCounter"] >= 2
+    # growth in the middle of a run: a passively relaxed (homogeneous) state has lists of <= ~21 entries; switching the
+    # propulsion on makes the density fluctuate and the longest list grows to ~35 within 200 steps (measured on the oracle)
+    o, _ = relaxed_oracle(N, rho, seed=9, l_s=0.0, l_n=0.3, presteps=100)
+    s = o.state()
+    o.close()
+    with device_from_state(s, seed=3, max_neighbors=24) as e, device_from_state(s, seed=3, max_neighbors=96) as g:
+        assert g.counters()["list_max"] <= 24
+        for q in (e, g):
+            q.set_activity(0.5, 0.3)
+            q.step(400)
+        assert g.counters()["list_max"] > 24, "the run was meant to outgrow the initial list capacity"
+        a, b = e.download(), g.download()
+        for f in ("x", "y", "cosp", "sinp", "x_old"):
+            assert np.array_equal(a[f], b[f]), f
+        assert e.counters()["resetCounter"] == g.counters()["resetCounter"] and e.counters()["overflow"] == 0
+
+
+def DeviceEngine_(*a, **k):
+    from active_particle_jamming_b200 import DeviceEngine
+    return DeviceEngine(*a, **k)
+
+
+def test_download_into_caller_buffers_and_checksum():
+    """apj_download_state scatters by id on the device into caller-owned (here page-locked) arrays; the
+    state fingerprint is a function of the state only (not of the memory order, which a rebuild changes)."""
+    import torch
+    N = 20000
+    o, _ = relaxed_oracle(N, 0.9, seed=8, presteps=10)
+    s = o.state()
+    o.close()
+    with device_from_state(s, seed=1) as e:
+        bufs = {k: torch.empty(N, dtype=torch.float64, pin_memory=True).numpy() for k in ("x", "y", "cosp", "sinp", "R", "phi")}
+        bufs["box"] = torch.empty(N, dtype=torch.int32, pin_memory=True).numpy()
+        d = e.download(list(bufs), out=bufs)
+        assert all(d[k] is bufs[k] for k in bufs)
+        for dev, orc in (("x", "x"), ("y", "y"), ("cosp", "cosp"), ("sinp", "sinp"), ("R", "R"), ("phi", "phi")):
+            assert np.array_equal(d[dev], s[orc]), dev                        # upload -> download is the identity
+        c0 = e.checksum()
+        e.force_rebuild()                                                     # permutes memory, not the state
+        assert e.checksum() == c0
+        e.step(3)
+        assert e.checksum() != c0
+        with pytest.raises(ValueError):
+            e.download(["x"], out={"x": np.zeros(N - 1)})
+    # phi only: cos/sin derived on the device (jamming.cpp:332-333), within an ulp of the host's
+    with DeviceEngine_(N, s["L"]) as e:
+        e.upload(x=s["x"], y=s["y"], R=s["R"], phi=s["phi"])
+        d = e.download(["cosp", "sinp", "x_real", "x0", "vx"])
+        assert np.max(np.abs(d["cosp"] - np.cos(s["phi"]))) <= 4e-16 and np.max(np.abs(d["sinp"] - np.sin(s["phi"]))) <= 4e-16
+        assert np.array_equal(d["x_real"], s["x"]) and np.array_equal(d["x0"], s["x"]) and not d["vx"].any()
+    # cos/sin only: phi derived
+    with DeviceEngine_(N, s["L"]) as e:
+        e.upload(x=s["x"], y=s["y"], R=s["R"], cosp=s["cosp"], sinp=s["sinp"])
+        assert np.max(np.abs(e.download(["phi"])["phi"] - np.arctan2(s["sinp"], s["cosp"]))) <= 1e-15
+
+
+def _pair_hash(off, idx, n, chunk=1 << 24):
+    """Order-independent 64-bit hash of the half-list pair set {(i, j)}: sum of a mixed (i << 32 | j)."""
+    rows = np.repeat(np.arange(n, dtype=np.uint64), np.diff(off))
+    acc = np.uint64(0)
+    with np.errstate(over="ignore"):
+        for a in range(0, rows.size, chunk):
+            z = (rows[a:a + chunk] << np.uint64(32)) | idx[a:a + chunk].astype(np.uint64)
+            z ^= z >> np.uint64(30); z *= np.uint64(0xbf58476d1ce4e5b9)
+            z ^= z >> np.uint64(27); z *= np.uint64(0x94d049bb133111eb)
+            z ^= z >> np.uint64(31)
+            acc += z.sum(dtype=np.uint64)
+    return int(acc)
+
+
+def test_headline_16m_box_parity():
+    """The configuration the metric is quoted on (BASELINE.json configs[3], bench workload box16m): N = 16 777 216,
+    phi = 0.9. Neighbour-pair set against the O(N) oracle -- per-particle half-list lengths array_equal, pair hash
+    equal, total equal -- and one injected-noise step <= 1e-12 (gates 1 and 2 of north_star at full size)."""
+    N, rho = 16777216, 0.9
+    R, L, x, y, phi = random_system(N, rho, 2026)
+    o = OracleSim.from_arrays(R, x, y, phi, rho)
+    o.set_params(0.05, 0.5)
+    o.topology(); o.assign(); o.build(); o.mark_origin()
+    off_o, idx_o = o.verlet()
+    from active_particle_jamming_b200 import DeviceEngine
+    with DeviceEngine(N, L, seed=4, max_neighbors=64) as e:
+        e.set_activity(0.05, 0.5)
+        e.upload(x=o.x, y=o.y, R=o.R, phi=o.phi, cosp=o.cosp, sinp=o.sinp)
+        e.skip_self_term_once()                                               # the oracle's first step has x_new = 0 (Cell.h:75,102)
+        assert np.array_equal(e.download(["box"])["box"], o.box)
+        off_d, idx_d = e.pair_list()
+        assert off_d[-1] == off_o[-1] == idx_o.size
+        assert np.array_equal(np.diff(off_d), np.diff(off_o))
+        assert _pair_hash(off_d, idx_d, N) == _pair_hash(off_o, idx_o, N)
+        del off_d, idx_d, off_o, idx_o
+        nz = np.random.default_rng(7).uniform(-PI, PI, N)
+        o.step(nz); e.step_injected(nz)
+        assert_state_close(e.download(), o, L, TOL, "16M step")
+        sc, c = o.scalars(), e.get_com()
+        assert abs(c["COM"][0] - sc["COMx"]) <= TOL * L and abs(c["COM"][1] - sc["COMy"]) <= TOL * L
+    o.close()
 
 
 def test_inhomogeneous_density_grows_the_tile():

@@ -87,6 +87,7 @@ def test_slab_free_running_bit_identical_to_periodic(nranks, lanes, N, flags):
         assert ce["resetCounter"] >= 3, "the run was meant to cross several rebuilds"
         if nranks > 1:
             assert moved > 0, "no particle ever changed rank: migration untested"
+        assert box.checksum() == e.checksum()                                # the fingerprint bench.py prints per --gpus N
         # observables: additive shares of the ranks against the periodic engine
         assert abs(box.order_orientation()[0][0] - e.order_orientation()[0][0]) <= TOL
         assert abs(box.msd()[0] - e.msd()[0]) <= TOL * max(1.0, e.msd()[0])

@@ -68,7 +68,7 @@ def test_driver_has_no_cpu_path(jam, tmp_path):
 
 def test_host_classes_never_compute_the_hot_path():
     src = open(os.path.join(HOST, "classes", "Cell.h")).read()
-    assert "exit(718)" in src                                # Cell::update aborts: the update is the kernel's epilogue
+    assert "exit(118)" in src                                # Cell::update aborts: the update is the kernel's epilogue
     drv = open(os.path.join(HOST, "jam", "jamming.cpp")).read() + open(os.path.join(HOST, "classes", "Batch.h")).read()
     for call in ("apj_step", "apj_force_rebuild", "apj_order_orientation", "apj_msd", "apj_mark_origin", "apj_fluct_area",
                  "apj_spatial_correlations", "apj_vel_hist", "apj_occupancy_hist"):
