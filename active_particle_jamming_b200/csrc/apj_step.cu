@@ -46,6 +46,37 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
     return v;
 }
 
+// 1/sqrt(a) for the overlap term: hardware approximation (rsqrt.approx.f64: ~20 good bits) refined by ONE
+// cubically convergent step, y1 = y0 + y0 e (1/2 + 3/8 e) with the residual e = 1 - a y0^2 formed by an fma:
+// truncation 5/16 e^3 < 2^-61, rounding ~1 ulp -- the accuracy of CUDA's rsqrt() (1 ulp) at a third of its
+// instructions and none of its special-case branches. a = 0 (coincident particles) gives NaN, as the
+// reference's inf * 0 does; denormal a does not occur (a is a squared distance of O(1)).
+__device__ __forceinline__ double apj_rsqrt(const double a) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+    const double h = a * y0;
+    const double e = fma(-h, y0, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double q = y0 * e;
+    return fma(q, p, y0);
+}
+
+// top-2 of one non-negative value per lane over the warp (the multiset newSkinList's scan keeps,
+// jamming.cpp:607-608). Non-negative doubles order like their bit patterns, so two 32-bit REDUX.MAX per
+// value replace the five shuffle + merge rounds.
+__device__ __forceinline__ void apj_warp_top2(const double v, double& t1, double& t2) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    const unsigned who = __ballot_sync(0xffffffffu, hi == mh && lo == ml);
+    const bool first = (int)(threadIdx.x & 31) == __ffs((int)who) - 1;       // one holder of the maximum steps aside
+    const unsigned hi2 = first ? 0u : hi, lo2 = first ? 0u : lo;
+    const unsigned nh = __reduce_max_sync(0xffffffffu, hi2);
+    const unsigned nl = __reduce_max_sync(0xffffffffu, hi2 == nh ? lo2 : 0u);
+    t1 = __hiloint2double((int)mh, (int)ml);
+    t2 = __hiloint2double((int)nh, (int)nl);
+}
+
 // one neighbour: reference jamming.cpp:633-662 seen from particle i (gather form). `off` is the
 // byte offset of the neighbour's 16-byte tile slot; offset 0 is the sentinel slot, parked at
 // (1e300, 1e300) so that it fails the d2 < rn2 test like any far particle.
@@ -54,10 +85,10 @@ __device__ __forceinline__ void pair_force(PairAcc& a, const double Ri, const do
                                            const unsigned at, const unsigned dCS, const unsigned dRR) {
     const double sumR = Ri + lds_f64(at + dRR);
     if (d2 < sumR * sumR) {                           // they also overlap (:641)
-        // overlap = sumR / sqrt(d2) - 1 (:643), evaluated as sumR * rsqrt(d2) - 1: rsqrt is
-        // correct to 1 ulp, so the quotient differs from the reference's by <= ~2 ulp
-        // (4e-16), far inside the 1e-12 gate, at a third of the instruction count.
-        const double overlap = sumR * rsqrt(d2) - 1;
+        // overlap = sumR / sqrt(d2) - 1 (:643), evaluated as sumR * rsqrt(d2) - 1: apj_rsqrt is
+        // good to ~1 ulp, so the quotient differs from the reference's by <= ~2 ulp
+        // (4e-16), far inside the 1e-12 gate, at a fraction of the instruction count.
+        const double overlap = sumR * apj_rsqrt(d2) - 1;
         a.Fx -= overlap * dx;
         a.Fy -= overlap * dy;
     }
@@ -168,7 +199,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     __shared__ double4 s_red[EWARPS];
 
     static_assert(!PERSIST || (SPLIT && G == 1), "the persistent form is the split-tail kernel of one large system");
-    const int sys = PERSIST ? 0 : blockIdx.x / st.maxblk;
+    const int sys = (PERSIST || st.n_sys == 1) ? 0 : blockIdx.x / st.maxblk;
     int blk = PERSIST ? (int)blockIdx.x : (int)(blockIdx.x - sys * st.maxblk);
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     long long bg = (long long)sys * st.maxblk + blk;
@@ -192,7 +223,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     if (blk >= nblk || ctl->stale || step >= ctl->target) return;  // uniform over the system's blocks
 
     const int cur = ctl->cur, gen = ctl->gen;
-    const int kcls = apj_sweep_class(ctl, st);         // distance classes this launch sweeps (0..kcls)
+    __shared__ int s_kcls;                             // distance classes this launch sweeps (0..kcls): uniform, derived by one thread
     int desc_next = 0;                                 // PERSIST: descriptor of this block's next tile, one tile ahead
     if (PERSIST && t < 16 && blk + (int)gridDim.x < nblk) desc_next = __ldg(reinterpret_cast<const int*>(st.tiles + bg + gridDim.x) + t);
     unsigned phase = 0;                                // parity of the tile mbarrier (flips per tile)
@@ -244,8 +275,9 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
             apj_bulk_g2s(dst + my_off, src + my_start, (unsigned)my_len * 16u, &s_bar);
         }
     }
-    if (t == 32 % TB && first) sXYp[0] = make_double2(1e300, 1e300);
+    if (t == 32 % TB && first) { sXYp[0] = make_double2(1e300, 1e300); s_kcls = apj_sweep_class(ctl, st); }
     __syncthreads();
+    const int kcls = s_kcls;
 
     const int npieces = sd.info & 0xff;
     const bool wraps = (sd.info & APJ_INFO_WRAPS) != 0;
@@ -432,9 +464,8 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     for (int o = 16; o > 0; o >>= 1) {
         sum_x += __shfl_xor_sync(0xffffffffu, sum_x, o);
         sum_y += __shfl_xor_sync(0xffffffffu, sum_y, o);
-        const double b1 = __shfl_xor_sync(0xffffffffu, top1, o), b2 = __shfl_xor_sync(0xffffffffu, top2, o);
-        apj_top2_merge(top1, top2, b1, b2);
     }
+    apj_warp_top2(top1, top1, top2);
     if (EWARPS > 1) {
         if (lane == 0) s_red[wid] = make_double4(sum_x, sum_y, top1, top2);
         __syncthreads();       // all EWARPS == all warps of the block when EWARPS > 1 (G == 1 or 2)
