@@ -34,13 +34,13 @@
 // rn once the two particles have moved d_b - rn relative to each other, and the relative
 // displacement of any pair since the build is bounded by the sum of the two largest COM-corrected
 // displacements -- the very quantity D = sqrt(l1)+sqrt(l2) the reference's skin test evaluates every
-// step (jamming.cpp:596-611). Lists are stored in APJ_CLASSES distance classes (class k: d_b < rn +
-// (k+1)*skin/APJ_CLASSES), so a step only has to sweep the classes with (k+1)*skin/APJ_CLASSES >= D.
+// step (jamming.cpp:596-611). Lists are stored in APJ_CLASSES classes of build distance, uniform in d_b^2
+// (class k = floor((d_b^2 - rn^2) * APJ_CLASSES / (rs^2 - rn^2)), class 0 also holds everything inside rn), so a
+// step only has to sweep the classes k <= ((rn + D)^2 - rn^2) * APJ_CLASSES / (rs^2 - rn^2).
 // The class is chosen from the previous step's D plus a margin and VERIFIED against the step's own D
 // at commit time; a launch that swept too few entries is dropped and re-run (same mechanism as the
 // speculative rebuild), so the result never differs from sweeping the full list.
 #define APJ_CLASSES 4
-#define APJ_CLASS_EPS 1e-9
 // TileDesc::info bits
 #define APJ_INFO_WRAPS (1 << 8)
 #define APJ_INFO_PUSH_LEFT (1 << 9)    // slab mode: the block's particles are the left neighbour's right ghost column
@@ -128,7 +128,7 @@ struct DevState {
     int max_quads;         // ceil(max_rounds / 4): uint4 rows of the per-block list array
     int tile_cap;          // shared-memory tile capacity in slots (<= 4094; slot 0 is the sentinel)
     double dt, rn2, rs2, skin;  // skin = rs - rn (jamming.cpp:611)
-    double cls2[APJ_CLASSES];   // (rn + (k+1)*skin/APJ_CLASSES)^2: upper bound of build distance^2 of class k (cls2[last] = rs2)
+    double rn, cls_inv;         // cls_inv = APJ_CLASSES / (rs^2 - rn^2): build-distance class of a list entry = floor((d2 - rn2) * cls_inv), >= 0
     int truncate;               // 0 disables the skin-aware sweep length (always the full list)
     int split_tail;             // 1: step kernel leaves per-block partials, apj_reduce_commit_kernel folds and commits (large systems)
     int want_persist;           // APJ_FLAG_PERSIST
@@ -239,19 +239,23 @@ __device__ __forceinline__ double apj_u32_to_randuni(unsigned u) {
     return __dadd_rn(__dmul_rn(__dmul_rn((double)u, 1.0 / 4294967296.0), APJ_PI - (-APJ_PI)), -APJ_PI);
 }
 
-// lowest distance class that is safe to stop after when the skin-test value is D (APJ_CLASSES-1 = full list)
-__device__ __forceinline__ int apj_class_for(double D, double skin) {
-    int k = 0;
-#pragma unroll
-    for (int c = 0; c < APJ_CLASSES - 1; c++)
-        if (D > (c + 1) * skin / APJ_CLASSES - APJ_CLASS_EPS) k = c + 1;
-    return k;
+// build-distance class of a list entry (apj_verlet_build_kernel): a pure function of d2, so the list order does
+// not depend on the decomposition
+__device__ __forceinline__ int apj_entry_class(double d2, double rn2, double cls_inv) {
+    return min(max((int)((d2 - rn2) * cls_inv), 0), APJ_CLASSES - 1);
+}
+// last distance class a step must sweep when the skin-test value is D (APJ_CLASSES-1 = full list): an entry of
+// class k was built at d_b^2 >= rn^2 + k / cls_inv and can only have come within rn if d_b <= rn + D
+__device__ __forceinline__ int apj_class_for(double D, const DevState& st) {
+    const double r = st.rn + D;
+    const double x = (r * r - st.rn2) * st.cls_inv + 1e-6;
+    return x >= (double)(APJ_CLASSES - 1) ? APJ_CLASSES - 1 : (int)x;
 }
 // class the launch sweeps: from the previous step's D plus a margin for this step's motion (uniform
 // over the blocks of a system: reads only fields no block writes before the commit)
 __device__ __forceinline__ int apj_sweep_class(const SysCtl* ctl, const DevState& st) {
     if (!st.truncate || !ctl->trunc_ok) return APJ_CLASSES - 1;
-    const int k = apj_class_for(ctl->skinD + 2.0 * ctl->skinDD + 0.01, st.skin);
+    const int k = apj_class_for(ctl->skinD + 2.0 * ctl->skinDD + 0.01, st);
     return k > ctl->kmin ? k : ctl->kmin;
 }
 
@@ -289,6 +293,12 @@ __device__ __forceinline__ void apj_mbar_expect_tx(unsigned long long* bar, unsi
 __device__ __forceinline__ void apj_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(apj_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(apj_smem_addr(bar)) : "memory");
+}
+// shared-state-space loads by 32-bit address (keeps gather loops free of generic->shared address arithmetic)
+__device__ __forceinline__ double2 apj_lds_f64x2(unsigned addr) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
 }
 // L2 prefetch hints (no data reaches the SM): one line / a contiguous range (16-byte granules)
 __device__ __forceinline__ void apj_prefetch_l2(const void* p) {

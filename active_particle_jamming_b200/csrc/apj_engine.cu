@@ -316,8 +316,7 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     const double rn = cfg->rn > 0 ? cfg->rn : 2.8;
     const double rs = (cfg->rs_factor > 0 ? cfg->rs_factor : 1.5) * rn;
     st.dt = dt; st.rn2 = rn * rn; st.rs2 = rs * rs; st.skin = rs - rn;
-    for (int k = 0; k < APJ_CLASSES; k++) { const double r = rn + (k + 1) * st.skin / APJ_CLASSES; st.cls2[k] = r * r; }
-    st.cls2[APJ_CLASSES - 1] = st.rs2;
+    st.rn = rn; st.cls_inv = APJ_CLASSES / (st.rs2 - st.rn2);
 #ifdef APJ_NO_TRUNCATE
     st.truncate = 0;
 #else

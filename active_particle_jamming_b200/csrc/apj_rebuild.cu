@@ -9,8 +9,9 @@
 //   cell_sort    sort each cell's slots by particle id (== Box::CellList ascending order;
 //                makes the layout, and with it every reduction order, deterministic)
 //   reorder      gather all SoA arrays through perm into the other ping-pong half
-//   make_tiles   cut every cell column into work blocks of <= ppb particles and record, per
-//                block, the contiguous particle runs that cover all adjacent cells (TileDesc)
+//   make_tiles   cut every cell column into work blocks of <= ppb particles (scan of the blocks per column),
+//   fill_tiles   then record, one thread per block, the contiguous particle runs that cover all adjacent
+//                cells (TileDesc)
 //   verlet_build 3x3 cell sweep out of a shared-memory tile, d2 < rs2, full list stored as tile slots,
 //                first coordination shell first
 //   finish       flip parities, COM_old = COM, resetCounter++, clear `stale`
@@ -48,15 +49,24 @@ __device__ __forceinline__ int2 nearest_box(const double2 me, const double L, co
     const int gx = (int)floor((me.x + Lh) / lp), gy = (int)floor((me.y + Lh) / lp);
     double r2 = lp * lp * 0.25 * 2;
     int bx = prev_x, by = prev_y;
-    for (int qy = gy - 1; qy <= gy + 1; qy++) {
+    // distances to the three candidate columns / rows, each centre evaluated once (the divisions dominate this kernel)
+    double ddx[3], ddy[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double drx = me.x - box_centre(gx - 1 + k, L, Lh, b), dry = me.y - box_centre(gy - 1 + k, L, Lh, b);
+        ddx[k] = drx * drx; ddy[k] = dry * dry;
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+        const int qy = gy - 1 + ky;
         if (qy < 0 || qy >= b) continue;
-        const double dry = me.y - box_centre(qy, L, Lh, b);
-        for (int qx = gx - 1; qx <= gx + 1; qx++) {
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+            const int qx = gx - 1 + kx;
             if (qx < 0 || qx >= b) continue;
-            const double drx = me.x - box_centre(qx, L, Lh, b);
             double d2 = 0.0;
-            d2 += drx * drx;
-            d2 += dry * dry;
+            d2 += ddx[kx];
+            d2 += ddy[ky];
             if (d2 < r2) { r2 = d2; bx = qx; by = qy; }
         }
     }
@@ -373,14 +383,12 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
     const int sys = blockIdx.x;
     SysCtl* __restrict__ ctl = st.ctl + sys;
     if (!ctl->stale) return;
-    const int b = ctl->b, w = ctl->ncols, col0 = ctl->col0;
+    const int b = ctl->b, w = ctl->ncols;
     const int* __restrict__ start = st.cell_start + ctl->cell_base;
-    const int* __restrict__ gs = st.slab ? st.gstart + (size_t)(ctl->gen ^ 1) * 2 * (b + 1) : nullptr;   // ghost columns [side][b+1]
     int* __restrict__ col_blk = st.col_blk + ctl->col_base;
-    const int* __restrict__ box = st.BOX[ctl->gen ^ 1];   // the half reorder just wrote
     __shared__ int s_warp[SCAN_BLOCK / 32];
-    __shared__ int s_carry, s_tile_max, s_over;
-    if (threadIdx.x == 0) { s_carry = 0; s_tile_max = 0; s_over = 0; }
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int ppb = st.ppb;
@@ -413,63 +421,83 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
         __syncthreads();
     }
     const int nblk = s_carry;
-    if (threadIdx.x == 0) col_blk[w] = nblk;
-    // descriptors: one thread per column walks that column's blocks
-    int tile_max = 0, over = 0;
-    for (int X = threadIdx.x; X < w; X += SCAN_BLOCK) {
-        const int c0 = start[X * b], c1 = start[(X + 1) * b];
-        const int Xg = X + col0;                           // column of the global grid
-        int blk = col_blk[X];
-        for (int g0 = c0; g0 < c1; g0 += ppb, blk++) {
-            TileDesc d;
-            d.g0 = g0; d.n = min(ppb, c1 - g0); d.own_slot = 0;
-            for (int p = 0; p < APJ_MAX_PIECES; p++) { d.pstart[p] = 0; d.plen[p] = 0; }
-            const int cy0 = box[g0] - X * b, cy1 = box[g0 + d.n - 1] - X * b;
-            int slots = 0, npieces = 0;
-            // minimum-image wraps can only fire in blocks that touch the periodic seam
-            int wraps = (b < 7 || Xg == 0 || Xg == b - 1 || cy0 == 0 || cy1 == b - 1) ? 1 : 0;
-            for (int dx = -1; dx <= 1; dx++) {
-                int Xd = X + dx;
-                const int* __restrict__ cs;
-                if (st.slab) {                             // beyond the slab: the neighbour's column, held as a ghost
-                    cs = Xd < 0 ? gs : (Xd >= w ? gs + (b + 1) : start + Xd * b);
-                } else {
-                    if (Xd < 0) Xd += b; else if (Xd >= b) Xd -= b;
-                    cs = start + Xd * b;
-                }
-                const int lo = cy0 - 1, hi = cy1 + 1;
-                const int before = slots;
-                int piece_of_own = -1;
-                if (hi - lo + 1 >= b) {                    // rows cover the whole column
-                    piece_of_own = npieces; add_piece(d, npieces, slots, cs[0], cs[b]);
-                } else if (lo < 0) {                       // wraps below: rows [0..hi] then [b-1]
-                    piece_of_own = npieces; add_piece(d, npieces, slots, cs[0], cs[hi + 1]);
-                    add_piece(d, npieces, slots, cs[lo + b], cs[b]);
-                } else if (hi > b - 1) {                   // wraps above: rows [lo..b-1] then [0]
-                    piece_of_own = npieces; add_piece(d, npieces, slots, cs[lo], cs[b]);
-                    add_piece(d, npieces, slots, cs[0], cs[hi - b + 1]);
-                } else {
-                    piece_of_own = npieces; add_piece(d, npieces, slots, cs[lo], cs[hi + 1]);
-                }
-                if (dx == 0)     // the block's own particles sit in the first piece of the middle column
-                    d.own_slot = 1 + before + (g0 - d.pstart[piece_of_own]);   // slots are 1-based (0 = sentinel)
-            }
-            d.info = npieces | (wraps ? APJ_INFO_WRAPS : 0);   // list words are filled in by verlet_build
-            if (st.slab && X == 0) d.info |= APJ_INFO_PUSH_LEFT;
-            if (st.slab && X == w - 1) d.info |= APJ_INFO_PUSH_RIGHT;
-            tile_max = max(tile_max, slots);
-            if (slots > st.tile_cap || slots > 4094) over = 1;   // 16-bit entries hold slot * 16
-            st.tiles[(long long)sys * st.maxblk + blk] = d;
-        }
-    }
-    if (tile_max) atomicMax(&s_tile_max, tile_max);
-    if (over) atomicOr(&s_over, 1);
-    __syncthreads();
     if (threadIdx.x == 0) {
+        col_blk[w] = nblk;
         ctl->nblk = nblk;
         ctl->last_col_start = start[(w - 1) * b];
-        ctl->tile_max = s_tile_max;
-        if (s_over) ctl->overflow |= 2;
+        ctl->tile_max = 0;
+    }
+}
+
+// descriptors: one thread per work block (column found by bisection of the per-column block offsets)
+__global__ void __launch_bounds__(RB_BLOCK) apj_fill_tiles_kernel(const DevState st) {
+    const int sys = blockIdx.y;
+    SysCtl* __restrict__ ctl = st.ctl + sys;
+    if (!ctl->stale) return;
+    const int blk = blockIdx.x * RB_BLOCK + threadIdx.x;
+    const int b = ctl->b, w = ctl->ncols, col0 = ctl->col0;
+    const int* __restrict__ col_blk = st.col_blk + ctl->col_base;
+    const int nblk = col_blk[w];
+    int slots = 0;
+    if (blk < nblk) {
+        const int* __restrict__ start = st.cell_start + ctl->cell_base;
+        const int* __restrict__ gs = st.slab ? st.gstart + (size_t)(ctl->gen ^ 1) * 2 * (b + 1) : nullptr;   // ghost columns [side][b+1]
+        const int* __restrict__ box = st.BOX[ctl->gen ^ 1];   // the half reorder just wrote
+        const int ppb = st.ppb;
+        int lo = 0, hi = w - 1;                            // last column X with col_blk[X] <= blk (empty columns share offsets)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (col_blk[mid] <= blk) lo = mid; else hi = mid - 1;
+        }
+        const int X = lo;
+        const int c1 = start[(X + 1) * b];
+        const int g0 = start[X * b] + (blk - col_blk[X]) * ppb;
+        const int Xg = X + col0;                           // column of the global grid
+        TileDesc d;
+        d.g0 = g0; d.n = min(ppb, c1 - g0); d.own_slot = 0;
+        for (int p = 0; p < APJ_MAX_PIECES; p++) { d.pstart[p] = 0; d.plen[p] = 0; }
+        const int cy0 = box[g0] - X * b, cy1 = box[g0 + d.n - 1] - X * b;
+        int npieces = 0;
+        // minimum-image wraps can only fire in blocks that touch the periodic seam
+        const int wraps = (b < 7 || Xg == 0 || Xg == b - 1 || cy0 == 0 || cy1 == b - 1) ? 1 : 0;
+        for (int dx = -1; dx <= 1; dx++) {
+            int Xd = X + dx;
+            const int* __restrict__ cs;
+            if (st.slab) {                             // beyond the slab: the neighbour's column, held as a ghost
+                cs = Xd < 0 ? gs : (Xd >= w ? gs + (b + 1) : start + Xd * b);
+            } else {
+                if (Xd < 0) Xd += b; else if (Xd >= b) Xd -= b;
+                cs = start + Xd * b;
+            }
+            const int lo_r = cy0 - 1, hi_r = cy1 + 1;
+            const int before = slots;
+            int piece_of_own = -1;
+            if (hi_r - lo_r + 1 >= b) {                // rows cover the whole column
+                piece_of_own = npieces; add_piece(d, npieces, slots, cs[0], cs[b]);
+            } else if (lo_r < 0) {                     // wraps below: rows [0..hi] then [b-1]
+                piece_of_own = npieces; add_piece(d, npieces, slots, cs[0], cs[hi_r + 1]);
+                add_piece(d, npieces, slots, cs[lo_r + b], cs[b]);
+            } else if (hi_r > b - 1) {                 // wraps above: rows [lo..b-1] then [0]
+                piece_of_own = npieces; add_piece(d, npieces, slots, cs[lo_r], cs[b]);
+                add_piece(d, npieces, slots, cs[0], cs[hi_r - b + 1]);
+            } else {
+                piece_of_own = npieces; add_piece(d, npieces, slots, cs[lo_r], cs[hi_r + 1]);
+            }
+            if (dx == 0)     // the block's own particles sit in the first piece of the middle column
+                d.own_slot = 1 + before + (g0 - d.pstart[piece_of_own]);   // slots are 1-based (0 = sentinel)
+        }
+        d.info = npieces | (wraps ? APJ_INFO_WRAPS : 0);
+        if (st.slab && X == 0) d.info |= APJ_INFO_PUSH_LEFT;
+        if (st.slab && X == w - 1) d.info |= APJ_INFO_PUSH_RIGHT;
+        st.tiles[(long long)sys * st.maxblk + blk] = d;
+    }
+    // largest tile of the decomposition / capacity check: one atomic per warp
+    int m = slots;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) {
+        atomicMax(&ctl->tile_max, m);
+        if (m > st.tile_cap || m > 4094) atomicOr(&ctl->overflow, 2);   // 16-bit entries hold slot * 16
     }
 }
 
@@ -485,23 +513,32 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
 // cntk[] holds the cumulative list length through each class. The pair SET is what the reference
 // defines (d2 < rs2); the order inside a list is ours.
 
-template <bool WRAP, class F>
-__device__ __forceinline__ void for_each_candidate(const TileDesc& sd, const int* __restrict__ start, const int* __restrict__ gs,
-                                                   const int w, const int b, const int cx,
-                                                   const int cy, const double2* __restrict__ sXY, const int own,
-                                                   const double2 me, const double L, const double Lh, const double rs2, F&& f) {
-    auto run = [&](int a, int e) {
-        if (e <= a) return;
-        const int s0 = apj_slot_of(sd, a);
-        for (int s = s0; s < s0 + (e - a); s++) {
-            if (s == own) continue;
-            const double2 q = sXY[s];
-            double dx = q.x - me.x, dy = q.y - me.y;
-            if (WRAP) { dx = apj_wrap1(dx, L, Lh); dy = apj_wrap1(dy, L, Lh); }
-            const double d2 = apj_d2(dx, dy);
-            if (d2 < rs2) f(s, d2);
-        }
-    };
+// One pass over the candidates, one thread per particle. Everything a hit triggers is predicated straight-line
+// code (class tag, 16-bit store into the thread's column of a shared-memory staging array, two counters), so the
+// lanes of a warp stay together for the whole 3x3 sweep; a second, short pass over the ~16 staged hits places
+// them in class-major order at their final position in the block's [quad][thread] list array. (Round 1 walked the
+// candidates twice with the placement inside a divergent branch: 333 warp-instructions per particle at 14 active
+// lanes, 6.5 ms at N = 16M; see profiles/r02_a_apj_verlet_build_kernel_ncu_full.txt.)
+template <bool WRAP>
+__device__ __forceinline__ void build_lists(const DevState& st, SysCtl* __restrict__ ctl, const TileDesc& sd, const long long bg,
+                                            const double2* __restrict__ sXY, unsigned short* __restrict__ stage, const int lgG) {
+    const int t = threadIdx.x, TBn = blockDim.x;
+    const int g = sd.g0 + t;
+    const int gen = ctl->gen ^ 1;                      // the half reorder just wrote
+    const int* __restrict__ start = st.cell_start + ctl->cell_base;
+    const int b = ctl->b, w = ctl->ncols;
+    const int* __restrict__ gs = st.slab ? st.gstart + (size_t)gen * 2 * (b + 1) : nullptr;
+    const double L = ctl->L, Lh = ctl->Lover2, rs2 = st.rs2, rn2 = st.rn2, cinv = st.cls_inv;
+    static_assert(APJ_CLASSES == 4, "class tags are two bits, cumulative counts four bytes");
+    const unsigned base = apj_smem_addr(sXY), a_own = base + (unsigned)(sd.own_slot + t) * 16u;
+    const double2 me = apj_lds_f64x2(a_own);
+    const int c = st.BOX[gen][g];
+    const int cx = c / b, cy = c - cx * b;
+    const int S = st.S;
+    const bool interior = cy >= 1 && cy <= b - 2;      // rows cy-1..cy+1 are one contiguous run of the column
+    const int nruns = interior ? 1 : 3;
+    int n = 0;                                         // hits so far (entries of the full list)
+    unsigned short* __restrict__ sp = stage + t;       // this thread's column of the staging array, one row per hit
     for (int dcx = -1; dcx <= 1; dcx++) {
         int col = cx + dcx;
         const int* __restrict__ cs;
@@ -511,86 +548,67 @@ __device__ __forceinline__ void for_each_candidate(const TileDesc& sd, const int
             if (col < 0) col += b; else if (col >= b) col -= b;
             cs = start + col * b;
         }
-        if (cy >= 1 && cy <= b - 2) {
-            run(cs[cy - 1], cs[cy + 2]);               // rows cy-1..cy+1 are one contiguous run
-        } else {
-            for (int dcy = -1; dcy <= 1; dcy++) {      // y wraps: row by row
-                int row = cy + dcy;
+        for (int r = 0; r < nruns; r++) {
+            int a, e;
+            if (interior) { a = cs[cy - 1]; e = cs[cy + 2]; }
+            else {                                     // y wraps: row by row
+                int row = cy - 1 + r;
                 if (row < 0) row += b; else if (row >= b) row -= b;
-                run(cs[row], cs[row + 1]);
+                a = cs[row]; e = cs[row + 1];
+            }
+            if (e <= a) continue;
+            // the loop runs on the shared-memory byte address of the candidate's slot: one induction variable
+            const unsigned a0 = base + (unsigned)apj_slot_of(sd, a) * 16u, a1 = a0 + (unsigned)(e - a) * 16u;
+            for (unsigned at = a0; at < a1; at += 16u) {
+                const double2 q = apj_lds_f64x2(at);
+                double dx = q.x - me.x, dy = q.y - me.y;
+                if (WRAP) { dx = apj_wrap1(dx, L, Lh); dy = apj_wrap1(dy, L, Lh); }
+                const double d2 = apj_d2(dx, dy);
+                if (d2 < rs2 && at != a_own) {
+                    *sp = (unsigned short)(((at - base) >> 2) | (unsigned)apj_entry_class(d2, rn2, cinv));   // slot << 2 | class
+                    n++;
+                    if (n < S) sp += TBn;              // a list that outgrows S keeps overwriting its last row: it is discarded below
+                }
             }
         }
     }
-}
-
-template <bool WRAP>
-__device__ __forceinline__ void build_lists(const DevState& st, SysCtl* __restrict__ ctl, const TileDesc& sd, const long long bg,
-                                            const double2* __restrict__ sXY) {
-    const int t = threadIdx.x;
-    const int g = sd.g0 + t;
-    const int gen = ctl->gen ^ 1;                      // the half reorder just wrote
-    const int* __restrict__ start = st.cell_start + ctl->cell_base;
-    const int b = ctl->b, w = ctl->ncols;
-    const int* __restrict__ gs = st.slab ? st.gstart + (size_t)gen * 2 * (b + 1) : nullptr;
-    const double L = ctl->L, Lh = ctl->Lover2, rs2 = st.rs2;
-    const int own = sd.own_slot + t;
-    const double2 me = sXY[own];
-    const int c = st.BOX[gen][g];
-    const int cx = c / b, cy = c - cx * b;
-    // two passes: count per distance class, then place (classes in order, slot order inside a class)
-    int ncls[APJ_CLASSES];
-#pragma unroll
-    for (int k = 0; k < APJ_CLASSES; k++) ncls[k] = 0;
-    auto cls_of = [&](double d2) {
-        int k = 0;
-#pragma unroll
-        for (int c = 0; c < APJ_CLASSES - 1; c++) if (!(d2 < st.cls2[c])) k = c + 1;
-        return k;
-    };
-    for_each_candidate<WRAP>(sd, start, gs, w, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int, double d2) {
-        const int k = cls_of(d2);
-#pragma unroll
-        for (int c = 0; c < APJ_CLASSES; c++) if (c == k) ncls[c]++;
-    });
-    int total = 0;
-    int cur_[APJ_CLASSES];                              // running write position of each class
-#pragma unroll
-    for (int k = 0; k < APJ_CLASSES; k++) { cur_[k] = total; total += ncls[k]; }
-    const int S = st.S, G = st.G;
-    const int n = min(total, S);
-    // entry e -> word e/2 -> lane (e/2) % G, that lane's word (e/2) / G, half e & 1
+    const int total = n;
+    const int nn = total <= S ? total : 0;             // a list that does not fit is not used at all (overflow is flagged below)
+    // hits per class (one byte each) -> cumulative counts for cntk, exclusive ones = running write position of each class
+    unsigned packed = 0;
+    for (int e = 0; e < nn; e++) packed += 1u << ((stage[e * TBn + t] & 3u) * 8u);
+    const unsigned k0 = packed & 0xffu, k1 = (packed >> 8) & 0xffu, k2 = (packed >> 16) & 0xffu;
+    const unsigned cum0 = k0, cum1 = cum0 + k1, cum2 = cum1 + k2;
+    unsigned cur = (cum0 << 8) | (cum1 << 16) | (cum2 << 24);
     unsigned short* __restrict__ out = reinterpret_cast<unsigned short*>(st.list32 + bg * (long long)st.max_quads * st.tb * 4);
+    const int G = 1 << lgG;
+    // entry e -> word e/2 -> lane (e/2) % G, that lane's word (e/2) / G, half e & 1
     auto put = [&](int e, unsigned v) {
-        const int w = e >> 1, sub = w % G, kk = w / G;
+        const int wd = e >> 1, sub = wd & (G - 1), kk = wd >> lgG;
         out[(((size_t)(kk >> 2) * st.tb + t * G + sub) * 4 + (kk & 3)) * 2 + (e & 1)] = (unsigned short)v;
     };
-    unsigned packed = 0;
-    {
-        int cum = 0;
-#pragma unroll
-        for (int k = 0; k < APJ_CLASSES; k++) { cum += ncls[k]; packed |= (unsigned)min(cum, S) << (8 * k); }
+    for (int e = 0; e < nn; e++) {
+        const unsigned v = stage[e * TBn + t];
+        const unsigned sh = (v & 3u) * 8u;
+        const int pos = (int)((cur >> sh) & 0xffu);
+        cur += 1u << sh;
+        put(pos, (v >> 2) << 4);
     }
-    for_each_candidate<WRAP>(sd, start, gs, w, b, cx, cy, sXY, own, me, L, Lh, rs2, [&](int s, double d2) {
-        const int k = cls_of(d2);
-        int e = 0;
-#pragma unroll
-        for (int c = 0; c < APJ_CLASSES; c++) if (c == k) e = cur_[c]++;
-        if (e < S) put(e, (unsigned)s << 4);
-    });
-    if (n & 1) put(n, 0u);                             // pad the last word with the sentinel
-    st.cnt[g] = n;
-    st.cntk[g] = packed;
-    if (total > S) ctl->overflow |= 1;                 // list capacity exceeded: reported by the host
+    if (nn & 1) put(nn, 0u);                           // pad the last word with the sentinel
+    st.cnt[g] = nn;
+    st.cntk[g] = total <= S ? (cum0 | (cum1 << 8) | (cum2 << 16) | ((unsigned)nn << 24)) : 0u;
+    if (total > S) ctl->overflow |= 1;                 // list capacity exceeded: the system stays stale, the host grows the storage
     if (total > ctl->list_max) atomicMax(&ctl->list_max, total);
 }
 
-__global__ void __launch_bounds__(APJ_TB_MAX) apj_verlet_build_kernel(const DevState st) {
+__global__ void __launch_bounds__(APJ_TB_MAX) apj_verlet_build_kernel(const DevState st, const int lgG) {
     const int sys = blockIdx.x / st.maxblk;
     const int blk = blockIdx.x - sys * st.maxblk;
     SysCtl* __restrict__ ctl = st.ctl + sys;
     if (!ctl->stale || blk >= ctl->nblk || (ctl->overflow & 2)) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* __restrict__ sXY = reinterpret_cast<double2*>(smem_raw);   // slot 0 unused here (slots are 1-based)
+    unsigned short* __restrict__ stage = reinterpret_cast<unsigned short*>(sXY + (st.tile_cap + 1));   // [S][blockDim.x]
     __shared__ TileDesc sd;
     __shared__ __align__(8) unsigned long long s_bar;
     const long long bg = (long long)sys * st.maxblk + blk;
@@ -612,8 +630,8 @@ __global__ void __launch_bounds__(APJ_TB_MAX) apj_verlet_build_kernel(const DevS
     unsigned dep = 0;
     apj_mbar_wait(&s_bar, 0, dep);
     if (threadIdx.x < sd.n) {
-        if (sd.info & APJ_INFO_WRAPS) build_lists<true>(st, ctl, sd, bg, sXY);
-        else build_lists<false>(st, ctl, sd, bg, sXY);
+        if (sd.info & APJ_INFO_WRAPS) build_lists<true>(st, ctl, sd, bg, sXY, stage, lgG);
+        else build_lists<false>(st, ctl, sd, bg, sXY, stage, lgG);
     }
 }
 
@@ -647,6 +665,7 @@ __global__ void apj_finish_rebuild_kernel(const DevState st) {
 
 }  // namespace
 
+size_t apj_build_smem_bytes(const DevState& st);
 void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nbox, int max_b) {
     (void)max_b;
     // fixed grids: ~16 blocks of 128 threads per SM in total, shared out over the systems
@@ -671,16 +690,21 @@ void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nb
         apj_slab_sync_kernel<<<1, 32, 0, l.stream>>>(st, 2);       // ghost columns in place on every rank
     }
     apj_make_tiles_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st);
-    apj_verlet_build_kernel<<<st.n_sys * st.maxblk, st.ppb, (size_t)(st.tile_cap + 1) * 16, l.stream>>>(st);
+    apj_fill_tiles_kernel<<<dim3((st.maxblk + RB_BLOCK - 1) / RB_BLOCK, st.n_sys), RB_BLOCK, 0, l.stream>>>(st);
+    int lgG = 0;
+    while ((1 << lgG) < st.G) lgG++;
+    apj_verlet_build_kernel<<<st.n_sys * st.maxblk, st.ppb, apj_build_smem_bytes(st), l.stream>>>(st, lgG);
     apj_finish_rebuild_kernel<<<(st.n_sys + 63) / 64, 64, 0, l.stream>>>(st);
     if (l.launch_counter) (*l.launch_counter) += apj_rebuild_chain_launches(st);
 }
-int apj_rebuild_chain_launches(const DevState& st) { return st.slab ? 14 : 10; }
+int apj_rebuild_chain_launches(const DevState& st) { return st.slab ? 15 : 11; }
 
 int apj_max_list_capacity() { return MAX_S; }
 int apj_scan_chunk_cells() { return SCAN_CHUNK; }
+// dynamic shared memory of the list build: the {x,y} tile + the staging array of 16-bit hits, [S][particles of the block]
+size_t apj_build_smem_bytes(const DevState& st) { return (size_t)(st.tile_cap + 1) * 16 + (size_t)st.S * st.ppb * 2; }
 int apj_configure_rebuild(const DevState& st) {
-    const int bytes = (st.tile_cap + 1) * 16;
+    const int bytes = (int)apj_build_smem_bytes(st);
     if (bytes <= 48 * 1024) return 0;
     return cudaFuncSetAttribute(apj_verlet_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : -1;
 }

@@ -365,7 +365,7 @@ def main():
     me.timer_begin(); e.force_rebuild(); reb_ms = max_over_ranks(me.timer_end())
     rebuild = {"ms_per_rebuild": reb_ms, "rebuilds_in_timed_region": nreb, "rebuilds_per_1000_steps": 1000.0 * nreb / K,
                "amortised_share_of_step": (nreb * reb_ms / K) / (ms / K) if ms > 0 else None,
-               "how": "CUDA events around one apj_force_rebuild (chain of %d launches + control read-back)" % (14 if slab else 10)}
+               "how": "CUDA events around one apj_force_rebuild (chain of %d launches + control read-back)" % (15 if slab else 11)}
 
     # ---- end to end: a whole job through the host-facing API, host buffers in, host buffers out
     e2e = None
