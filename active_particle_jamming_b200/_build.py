@@ -6,7 +6,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 # APJ_B200_LIB selects an experimental build variant by file name (tuning runs only)
 LIB = os.path.join(PKG, "lib", os.environ.get("APJ_B200_LIB", "libapj_b200.so"))
-SOURCES = ["apj_engine.cu", "apj_step.cu", "apj_rebuild.cu", "apj_observe.cu", "apj_state_io.cu"]
+SOURCES = ["apj_engine.cu", "apj_step.cu", "apj_rebuild.cu", "apj_observe.cu", "apj_state_io.cu", "apj_setup.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               # no FMA contraction in our own arithmetic: every product/sum rounds like the reference's
               # x86-64 build, so distance predicates and force terms match it bit for bit (CUDA libm

@@ -233,6 +233,18 @@ __device__ __forceinline__ unsigned apj_philox_word0(unsigned c0, unsigned c1, u
     }
     return c0;
 }
+// all four output words (device-side initCells draws several variates per particle)
+__device__ __forceinline__ uint4 apj_philox4(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
 // boost::uniform_real<>(-PI, PI) over a 32-bit engine (Boost 1.64 generate_uniform_real):
 // u / 2^32 * (PI - (-PI)) + (-PI)   
 __device__ __forceinline__ double apj_u32_to_randuni(unsigned u) {
@@ -300,6 +312,20 @@ __device__ __forceinline__ double2 apj_lds_f64x2(unsigned addr) {
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
+// 32-bit load that asks L2 to keep the line (evict_last policy): the tile descriptors are re-read every step while
+// ~3 GB of particle data stream through the 126 MB L2 in between; 4 MB of descriptors stay resident this way and
+// the head of a step block saves one trip to HBM.
+__device__ __forceinline__ int apj_ldg_l2keep(const int* p) {
+#ifdef APJ_NO_L2KEEP
+    return __ldg(p);
+#else
+    int v;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+#endif
+}
 // L2 prefetch hints (no data reaches the SM): one line / a contiguous range (16-byte granules)
 __device__ __forceinline__ void apj_prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -334,16 +360,44 @@ struct ApjStage {
     int* flag;
 };
 
+// APJ_DEBUG_LAUNCH=1: report the first kernel launch that fails, by name (launch errors are otherwise picked up by
+// the next cudaGetLastError of the calling ABI function)
+#include <cstdio>
+#include <cstdlib>
+inline void apj_check_launch(const char* what) {
+    static const int on = getenv("APJ_DEBUG_LAUNCH") ? atoi(getenv("APJ_DEBUG_LAUNCH")) : 0;
+    if (!on) return;
+    const cudaError_t s = cudaPeekAtLastError();
+    if (s != cudaSuccess) fprintf(stderr, "apj_b200: launch of %s failed: %s\n", what, cudaGetErrorString(s));
+}
+
+// Opt a kernel in to the device's full dynamic shared memory, once. The attribute is per FUNCTION, not per handle:
+// setting it to what one handle needs would undercut another handle of the same process with a larger tile.
+template <class K>
+inline bool apj_allow_max_smem(K kernel) {
+    int dev = 0, optin = 0;
+    cudaFuncAttributes fa;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return false;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes) == cudaSuccess;
+}
+
 // host-side launchers (one per .cu)
 struct ApjLaunch { cudaStream_t stream; long long* launch_counter; };
 void apj_launch_pack(const DevState& st, cudaStream_t s, const ApjStage& sg, unsigned present, long long n, int slab);
 void apj_launch_unpack(const DevState& st, cudaStream_t s, const ApjStage& sg, unsigned want, int by_id);
 void apj_launch_checksum(const DevState& st, cudaStream_t s, unsigned long long* out);
+// device-side initCells / topology / overlap hue (apj_setup.cu)
+void apj_launch_radii_sums(cudaStream_t s, long long n, int n_sys, unsigned long long seed, double* d_part, double* d_sum);
+void apj_launch_init_lattice(const DevState& st, cudaStream_t s, unsigned long long seed);
+void apj_launch_box_table(const DevState& st, cudaStream_t s, int sys, double* d_centres, int* d_neighbors);
+void apj_launch_overlap_hue(const DevState& st, cudaStream_t s, int* d_over_by_id);
 void apj_launch_step(const DevState& st, const ApjLaunch& l, const double* noise_by_id, int always_full);
 void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nbox, int max_b);
 int apj_rebuild_chain_launches(const DevState& st);
 int apj_configure_kernels(DevState& st);   // also sets st.persist_grid
 int apj_configure_rebuild(const DevState& st);
 int apj_step_blocks_per_sm_limit(int tb);   // __launch_bounds__ of the step kernel
+size_t apj_step_extra_smem(const DevState& st);   // dynamic shared memory of a step block beyond the tile
 int apj_max_list_capacity();
 int apj_scan_chunk_cells();

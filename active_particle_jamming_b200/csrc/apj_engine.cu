@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -142,7 +143,7 @@ static int build_group_graph(apj_engine* e);
 // when a rebuild produced a tile larger than the capacity (nothing was committed, the system is
 // still stale) or when a smaller capacity would fit one more block per SM.
 static int blocks_per_sm(const DevState& st, int cap) {
-    const size_t per_block = (size_t)(cap + 1) * 48 + (st.G > 1 ? (size_t)st.ppb * 32 : 0) + 1024 + 512;
+    const size_t per_block = (size_t)(cap + 1) * 48 + (st.G > 1 ? (size_t)st.ppb * 32 : 0) + apj_step_extra_smem(st) + 1024 + 1024;
     const int by_smem = (int)((size_t)233472 / per_block);
     return std::max(1, std::min(by_smem, apj_step_blocks_per_sm_limit(st.tb)));   // register file: __launch_bounds__ of the step kernel
 }
@@ -355,6 +356,17 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     e->total_cells = cells;
     e->total_cols = cols;
     st.maxblk = st.cap / st.ppb + e->max_b + 1;
+    st.maxgrp = (st.maxblk + 31) / 32;
+    // Large systems end the step with a separate fold + commit kernel (apj_step.cu); small ones (phase-diagram
+    // replicas, tests) are launch-bound and keep the commit fused into the step kernel's last block.
+#ifndef APJ_SPLIT_MIN_BLOCKS
+#define APJ_SPLIT_MIN_BLOCKS 4096
+#endif
+    st.split_tail = (st.G == 1 && (long long)st.n_sys * st.maxblk >= APJ_SPLIT_MIN_BLOCKS && st.maxblk <= 1024 * 1024) ? 1 : 0;
+    if (st.G == 1 && (cfg->flags & APJ_FLAG_SPLIT_TAIL) && st.maxblk <= 1024 * 1024) st.split_tail = 1;
+    if (cfg->flags & APJ_FLAG_FUSED_TAIL) st.split_tail = 0;
+    st.want_persist = (cfg->flags & APJ_FLAG_PERSIST) ? 1 : 0;
+    if (const char* pe = getenv("APJ_STEP_PIPE")) st.want_persist = atoi(pe) ? 1 : 0;   // tuning runs: force the pipelined kernel on / off
     {   // tile capacity: three columns x (block rows + 2 halo rows), sized from the mean cell occupancy
         double ppc = 0;
         for (int s = 0; s < st.n_sys; s++) ppc = std::max(ppc, (double)st.N / ((double)e->hctl[s].b * e->hctl[s].b));
@@ -396,16 +408,6 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     A(dev_alloc(e, &st.cell_start, (size_t)cells));
     A(dev_alloc(e, &st.cell_cursor, (size_t)cells));
     A(dev_alloc(e, &st.partials, (size_t)st.n_sys * st.maxblk));
-    st.maxgrp = (st.maxblk + 31) / 32;
-    // Large systems end the step with a separate fold + commit kernel (apj_step.cu); small ones (phase-diagram
-    // replicas, tests) are launch-bound and keep the commit fused into the step kernel's last block.
-#ifndef APJ_SPLIT_MIN_BLOCKS
-#define APJ_SPLIT_MIN_BLOCKS 4096
-#endif
-    st.split_tail = (st.G == 1 && (long long)st.n_sys * st.maxblk >= APJ_SPLIT_MIN_BLOCKS && st.maxblk <= 1024 * 1024) ? 1 : 0;
-    if (st.G == 1 && (cfg->flags & APJ_FLAG_SPLIT_TAIL) && st.maxblk <= 1024 * 1024) st.split_tail = 1;
-    if (cfg->flags & APJ_FLAG_FUSED_TAIL) st.split_tail = 0;
-    st.want_persist = (cfg->flags & APJ_FLAG_PERSIST) ? 1 : 0;
     A(dev_alloc(e, &st.gpartials, (size_t)st.n_sys * st.maxgrp));
     A(dev_alloc(e, &st.gticket, (size_t)st.n_sys * st.maxgrp));
     A(dev_alloc(e, &e->d_noise, (size_t)st.n_sys * st.N));
@@ -585,6 +587,80 @@ extern "C" int apj_download_state(apj_engine* e, apj_state* h) {
     return pull_ctl(e);                                   // synchronises the stream; refreshes hctl (checkpoint writer)
 }
 
+// ---- Engine::initCells / Engine::topology on the device (apj_setup.cu) -------------------------------------
+extern "C" int apj_lattice_box_length(int64_t n, int32_t n_systems, uint64_t seed, const double* dens, int32_t device, double* L_out) {
+    if (n < 1 || n_systems < 1 || !dens || !L_out) return fail(nullptr, APJ_E_INVALID, "apj_lattice_box_length: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, APJ_E_CUDA, "apj_lattice_box_length: no CUDA device (this library has no CPU fallback)");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, APJ_E_CUDA, "apj_lattice_box_length: cudaSetDevice failed");
+    double *d_part = nullptr, *d_sum = nullptr;
+    std::vector<double> sums(n_systems);
+    bool ok = cudaMalloc(&d_part, sizeof(double) * 1024 * (size_t)n_systems) == cudaSuccess && cudaMalloc(&d_sum, sizeof(double) * (size_t)n_systems) == cudaSuccess;
+    if (ok) {
+        apj_launch_radii_sums(nullptr, n, n_systems, seed, d_part, d_sum);
+        ok = cudaMemcpy(sums.data(), d_sum, sizeof(double) * (size_t)n_systems, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    cudaFree(d_part); cudaFree(d_sum);
+    if (!ok) return fail(nullptr, APJ_E_CUDA, "apj_lattice_box_length: CUDA error");
+    for (int s = 0; s < n_systems; s++) L_out[s] = std::sqrt(APJ_PI * sums[s] / dens[s]);   // jamming.cpp:305
+    return APJ_OK;
+}
+
+extern "C" int apj_init_lattice(apj_engine* e, uint64_t seed) {
+    if (!e) return APJ_E_INVALID;
+    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_init_lattice: periodic handles only (upload the slabs of a box initialised elsewhere)");
+    DevState& st = e->st;
+    if (int rc = pull_ctl(e)) return rc;
+    apj_launch_init_lattice(st, e->stream, seed);
+    e->launches++;
+    for (auto& c : e->hctl) {
+        c.cur = 0; c.gen = 0; c.stale = 1; c.save_old = 0; c.ticket = 0; c.overflow = 0; c.list_max = 0;
+        c.target = c.step; c.trunc_ok = 0;
+    }
+    APJ_CUDA(e, cudaMemsetAsync(st.cell_count, 0, sizeof(int) * e->total_cells, e->stream));
+    if (int rc = push_ctl(e)) return rc;
+    e->have_state = true;
+    std::vector<double> com(2 * st.n_sys);                        // COM = mean(x_real), fixed-order device reduction
+    if (int rc = apj_obs_com(&e->obs, st, e->stream, &e->launches, com.data())) return fail(e, rc, "apj_init_lattice: COM reduction failed");
+    for (int s = 0; s < st.n_sys; s++) {
+        SysCtl& c = e->hctl[s];
+        c.COM[0] = com[2 * s]; c.COM[1] = com[2 * s + 1];
+        c.COM0[0] = c.COM_old[0] = c.COM[0]; c.COM0[1] = c.COM_old[1] = c.COM[1];
+    }
+    if (int rc = push_ctl(e)) return rc;
+    return run_chain_now(e);                                      // assignCellsToGrid + buildVerletLists (start() :184-185)
+}
+
+extern "C" int apj_get_box_table(apj_engine* e, int32_t s, double* centres, int32_t* neighbors) {
+    if (!e || s < 0 || s >= e->st.n_sys || !centres || !neighbors) return APJ_E_INVALID;
+    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_get_box_table: periodic handles only");
+    const size_t nbox = (size_t)e->hctl[s].nbox;
+    double* dc = nullptr; int* dn = nullptr;
+    APJ_CUDA(e, cudaMalloc(&dc, sizeof(double) * 2 * nbox));
+    if (cudaMalloc(&dn, sizeof(int) * 9 * nbox) != cudaSuccess) { cudaFree(dc); return fail(e, APJ_E_CUDA, "apj_get_box_table: out of device memory"); }
+    apj_launch_box_table(e->st, e->stream, s, dc, dn);
+    e->launches++;
+    cudaError_t a = cudaMemcpyAsync(centres, dc, sizeof(double) * 2 * nbox, cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t b = cudaMemcpyAsync(neighbors, dn, sizeof(int) * 9 * nbox, cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t c = cudaStreamSynchronize(e->stream);
+    cudaFree(dc); cudaFree(dn);
+    if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess) return fail(e, APJ_E_CUDA, "apj_get_box_table: CUDA error");
+    return APJ_OK;
+}
+
+extern "C" int apj_overlap_hue(apj_engine* e, int32_t* over) {
+    if (!e || !over) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_overlap_hue: no state uploaded");
+    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_overlap_hue: periodic handles only");
+    const size_t n = (size_t)e->st.ntot;
+    if (int rc = ensure_stage(e, n)) return rc;
+    apj_launch_overlap_hue(e->st, e->stream, e->stage.box);       // staging plane reused: n ints by particle id
+    e->launches++;
+    APJ_CUDA(e, cudaMemcpyAsync(over, e->stage.box, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    return APJ_OK;
+}
+
 // 64-bit fingerprint of {id, x, y, cos, sin} summed over the owned particles: independent of particle order
 // and of the slab decomposition (ranks add their shares modulo 2^64).
 extern "C" int apj_state_checksum(apj_engine* e, uint64_t* out) {
@@ -658,8 +734,13 @@ extern "C" int apj_mark_origin(apj_engine* e) {
 // buildVerletLists without the skin bookkeeping), keeps x_old / COM_old, and continues the Philox stream
 // at the stored step. The continuation equals the uninterrupted run to rounding (first step <= 1e-12;
 // list order, hence summation order, differs after the fresh rebuild) -- not bit for bit.
+extern "C" int apj_slab_upload(apj_engine* e, const apj_state* h, const int32_t* ids, int64_t n_local);
+extern "C" int apj_slab_download(apj_engine* e, apj_state* h, int32_t* ids, int64_t cap, int64_t* n_local);
 namespace {
 struct CkptHeader { char magic[8]; int64_t n; int32_t n_sys, version; uint64_t seed; double dt, rn2, rs2; };
+// slab handles: one file per rank -- the rank's owned particles in device order with their ids. version = 2,
+// n_sys carries nranks, `rank` and `n_local` follow the common header.
+struct CkptSlab { int32_t rank, nranks; int64_t n_local; };
 struct CkptSys { int64_t step, reset_counter, ramp_len, ramp_t0; double L, CFself, CTnoise, COM[2], COM0[2], COM_old[2]; };
 const char CKPT_MAGIC[8] = {'A', 'P', 'J', 'C', 'K', 'P', 'T', '1'};
 }
@@ -667,8 +748,38 @@ const char CKPT_MAGIC[8] = {'A', 'P', 'J', 'C', 'K', 'P', 'T', '1'};
 extern "C" int apj_save_checkpoint(apj_engine* e, const char* path) {
     if (!e || !path) return APJ_E_INVALID;
     if (!e->have_state) return fail(e, APJ_E_STATE, "apj_save_checkpoint: no state uploaded");
-    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_save_checkpoint: slab handle (download the ranks and save a periodic box)");
     const DevState& st = e->st;
+    if (st.slab) {   // this rank's share: every rank writes its own file (the caller names them apart)
+        int64_t nl = 0;
+        apj_state q = {};
+        if (int rc = apj_slab_download(e, &q, nullptr, 0, &nl)) return rc;
+        const size_t T = (size_t)std::max<int64_t>(nl, 1);
+        std::vector<double> f[14];
+        for (auto& v : f) v.resize(T);
+        std::vector<int32_t> ids(T);
+        apj_state h = {};
+        h.x = f[0].data(); h.y = f[1].data(); h.x_real = f[2].data(); h.y_real = f[3].data(); h.x0 = f[4].data(); h.y0 = f[5].data();
+        h.x_old = f[6].data(); h.y_old = f[7].data(); h.R = f[8].data(); h.phi = f[9].data(); h.cosp = f[10].data(); h.sinp = f[11].data();
+        h.vx = f[12].data(); h.vy = f[13].data();
+        if (int rc = apj_slab_download(e, &h, ids.data(), (int64_t)T, &nl)) return rc;   // also refreshes hctl
+        FILE* fp = fopen(path, "wb");
+        if (!fp) return fail(e, APJ_E_INVALID, "apj_save_checkpoint: cannot open the file for writing");
+        CkptHeader hd = {};
+        memcpy(hd.magic, CKPT_MAGIC, 8);
+        hd.n = st.N; hd.n_sys = st.nranks; hd.version = 2; hd.seed = st.seed; hd.dt = st.dt; hd.rn2 = st.rn2; hd.rs2 = st.rs2;
+        CkptSlab sl = {st.rank, st.nranks, nl};
+        const SysCtl& c = e->hctl[0];
+        CkptSys cs = {};
+        cs.step = c.step; cs.reset_counter = c.reset_counter; cs.ramp_len = c.ramp_len; cs.ramp_t0 = c.ramp_t0;
+        cs.L = c.L; cs.CFself = c.CFself; cs.CTnoise = c.CTnoise;
+        for (int k = 0; k < 2; k++) { cs.COM[k] = c.COM[k]; cs.COM0[k] = c.COM0[k]; cs.COM_old[k] = c.COM_old[k]; }
+        const size_t n = (size_t)nl;
+        bool ok = fwrite(&hd, sizeof hd, 1, fp) == 1 && fwrite(&sl, sizeof sl, 1, fp) == 1 && fwrite(&cs, sizeof cs, 1, fp) == 1;
+        ok = ok && fwrite(ids.data(), sizeof(int32_t), n, fp) == n;
+        for (auto& v : f) ok = ok && fwrite(v.data(), sizeof(double), n, fp) == n;
+        ok = (fclose(fp) == 0) && ok;
+        return ok ? APJ_OK : fail(e, APJ_E_INVALID, "apj_save_checkpoint: short write");
+    }
     const size_t T = (size_t)st.n_sys * st.N;
     std::vector<double> f[14];
     for (auto& v : f) v.resize(T);
@@ -700,14 +811,45 @@ extern "C" int apj_save_checkpoint(apj_engine* e, const char* path) {
 
 extern "C" int apj_load_checkpoint(apj_engine* e, const char* path) {
     if (!e || !path) return APJ_E_INVALID;
-    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_load_checkpoint: slab handle");
     DevState& st = e->st;
     FILE* fp = fopen(path, "rb");
     if (!fp) return fail(e, APJ_E_INVALID, "apj_load_checkpoint: cannot open the file");
     CkptHeader hd;
-    if (fread(&hd, sizeof hd, 1, fp) != 1 || memcmp(hd.magic, CKPT_MAGIC, 8) != 0 || hd.version != 1) {
+    if (fread(&hd, sizeof hd, 1, fp) != 1 || memcmp(hd.magic, CKPT_MAGIC, 8) != 0 || hd.version != (st.slab ? 2 : 1)) {
         fclose(fp);
-        return fail(e, APJ_E_INVALID, "apj_load_checkpoint: not an APJCKPT1 file");
+        return fail(e, APJ_E_INVALID, st.slab ? "apj_load_checkpoint: not a slab-rank APJCKPT1 file" : "apj_load_checkpoint: not an APJCKPT1 file of a periodic box");
+    }
+    if (st.slab) {   // [collective] every rank loads the file its rank wrote
+        CkptSlab sl;
+        CkptSys cs;
+        bool ok = fread(&sl, sizeof sl, 1, fp) == 1 && fread(&cs, sizeof cs, 1, fp) == 1;
+        if (!ok || hd.n != st.N || hd.n_sys != st.nranks || sl.rank != st.rank || sl.nranks != st.nranks || hd.dt != st.dt || hd.rn2 != st.rn2 ||
+            hd.rs2 != st.rs2 || cs.L != e->hctl[0].L || sl.n_local < 0 || sl.n_local > st.cap) {
+            fclose(fp);
+            return fail(e, APJ_E_INVALID, "apj_load_checkpoint: the file was written by another rank / decomposition / shape");
+        }
+        const size_t n = (size_t)sl.n_local, T = std::max<size_t>(n, 1);
+        std::vector<int32_t> ids(T);
+        std::vector<double> f[14];
+        ok = fread(ids.data(), sizeof(int32_t), n, fp) == n;
+        for (auto& v : f) { v.resize(T); ok = ok && fread(v.data(), sizeof(double), n, fp) == n; }
+        fclose(fp);
+        if (!ok) return fail(e, APJ_E_INVALID, "apj_load_checkpoint: truncated file");
+        apj_state h = {};
+        h.x = f[0].data(); h.y = f[1].data(); h.x_real = f[2].data(); h.y_real = f[3].data(); h.x0 = f[4].data(); h.y0 = f[5].data();
+        h.x_old = f[6].data(); h.y_old = f[7].data(); h.R = f[8].data(); h.phi = f[9].data(); h.cosp = f[10].data(); h.sinp = f[11].data();
+        h.vx = f[12].data(); h.vy = f[13].data();
+        if (int rc = apj_slab_upload(e, &h, ids.data(), sl.n_local)) return rc;     // collective: ghost columns, lists
+        if (int rc = pull_ctl(e)) return rc;
+        SysCtl& c = e->hctl[0];
+        c.step = c.target = cs.step; c.reset_counter = cs.reset_counter; c.ramp_len = cs.ramp_len; c.ramp_t0 = cs.ramp_t0;
+        c.CFself = cs.CFself; c.CTnoise = cs.CTnoise;
+        for (int k = 0; k < 2; k++) { c.COM[k] = cs.COM[k]; c.COM0[k] = cs.COM0[k]; c.COM_old[k] = cs.COM_old[k]; }
+        c.no_self_once = 0;
+        c.trunc_ok = 0;
+        e->st.seed = hd.seed;
+        if (int rc = push_ctl(e)) return rc;
+        return build_group_graph(e);
     }
     if (hd.n != st.N || hd.n_sys != st.n_sys || hd.dt != st.dt || hd.rn2 != st.rn2 || hd.rs2 != st.rs2) {
         fclose(fp);
@@ -1010,6 +1152,23 @@ extern "C" int apj_fluct_area(apj_engine* e, const double* radius, double* area)
     APJ_NEED_STATE("apj_fluct_area");
     if (!radius || !area) return APJ_E_INVALID;
     APJ_OBS(apj_obs_fluct(&e->obs, e->st, e->stream, &e->launches, radius, area));
+}
+extern "C" int apj_obs_enqueue(apj_engine* e, int32_t kind, const double* param, int64_t* ticket) {
+    APJ_NEED_STATE("apj_obs_enqueue");
+    long long tk = 0;
+    const int rc = apj_obs_enqueue_ring(&e->obs, e->st, e->stream, &e->launches, kind, param, &tk);
+    if (rc == -1) return fail(e, APJ_E_INVALID, "apj_obs_enqueue: kind must be APJ_OBS_COM..APJ_OBS_FLUCT (FLUCT needs the radii)");
+    if (rc) return fail(e, rc, cudaGetErrorString(cudaGetLastError()));
+    if (ticket) *ticket = tk;
+    return APJ_OK;
+}
+extern "C" int apj_obs_fetch(apj_engine* e, int64_t first_ticket, int64_t count, double* out) {
+    APJ_NEED_STATE("apj_obs_fetch");
+    if (!out && count > 0) return APJ_E_INVALID;
+    const int rc = apj_obs_fetch_ring(&e->obs, e->st, e->stream, first_ticket, count, out);
+    if (rc == -1) return fail(e, APJ_E_INVALID, "apj_obs_fetch: tickets not issued yet, or already overwritten (the ring holds the last 4096)");
+    if (rc) return fail(e, rc, cudaGetErrorString(cudaGetLastError()));
+    return APJ_OK;
 }
 extern "C" int apj_spatial_correlations(apj_engine* e, double cutoff, double* counts, double* ori, double* vel, double* pair) {
     APJ_NEED_STATE("apj_spatial_correlations");

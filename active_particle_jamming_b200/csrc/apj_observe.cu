@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(OB) apj_spatial_kernel(const DevState st, cons
     for (int k = threadIdx.x; k < nb; k += OB) if (sh[k] != 0.0) atomicAdd(&acc[(size_t)sys * nb + k], sh[k]);
 }
 
-int reduce2(ApjObsScratch* o, const DevState& st, cudaStream_t s, long long* launches, int mode, const double* h_param, double* h_out2) {
+// queue one two-level reduction on the stream; its 2 * n_sys raw sums land in d_dst (no host synchronisation)
+int enqueue2(ApjObsScratch* o, const DevState& st, cudaStream_t s, long long* launches, int mode, const double* h_param, double* d_dst) {
     const int bps = o->blocks_per_sys;
     if (h_param) if (cudaMemcpyAsync(o->d_param, h_param, sizeof(double) * st.n_sys, cudaMemcpyHostToDevice, s) != cudaSuccess) return APJ_E_CUDA_OBS;
     const int grid = st.n_sys * bps;
@@ -186,8 +187,12 @@ int reduce2(ApjObsScratch* o, const DevState& st, cudaStream_t s, long long* lau
         case OBS_MSD: apj_obs_reduce_kernel<OBS_MSD><<<grid, OB, 0, s>>>(st, bps, o->d_param, o->d_part); break;
         default: apj_obs_reduce_kernel<OBS_FLUCT><<<grid, OB, 0, s>>>(st, bps, o->d_param, o->d_part); break;
     }
-    apj_obs_final_kernel<<<st.n_sys, OB, 0, s>>>(bps, o->d_part, o->d_out);
+    apj_obs_final_kernel<<<st.n_sys, OB, 0, s>>>(bps, o->d_part, d_dst);
     if (launches) *launches += 2;
+    return cudaGetLastError() == cudaSuccess ? 0 : APJ_E_CUDA_OBS;
+}
+int reduce2(ApjObsScratch* o, const DevState& st, cudaStream_t s, long long* launches, int mode, const double* h_param, double* h_out2) {
+    if (int rc = enqueue2(o, st, s, launches, mode, h_param, o->d_out)) return rc;
     if (cudaMemcpyAsync(h_out2, o->d_out, sizeof(double) * 2 * st.n_sys, cudaMemcpyDeviceToHost, s) != cudaSuccess) return APJ_E_CUDA_OBS;
     if (cudaStreamSynchronize(s) != cudaSuccess) return APJ_E_CUDA_OBS;
     return 0;
@@ -207,6 +212,34 @@ int apj_obs_alloc(ApjObsScratch* o, const DevState& st, cudaStream_t stream, std
     if (A((void**)&o->d_out, sizeof(double) * 2 * (size_t)st.n_sys)) return APJ_E_CUDA_OBS;
     if (A((void**)&o->d_param, sizeof(double) * (size_t)st.n_sys)) return APJ_E_CUDA_OBS;
     if (A((void**)&o->d_hist, sizeof(unsigned long long) * 128 * (size_t)st.n_sys)) return APJ_E_CUDA_OBS;
+    o->ring_cap = APJ_OBS_RING;
+    if (A((void**)&o->d_ring, sizeof(double) * 2 * (size_t)st.n_sys * o->ring_cap)) return APJ_E_CUDA_OBS;
+    return 0;
+}
+
+// Queued observables: the reduction is placed on the stream behind the steps already queued and its raw sums go
+// to slot (ticket % ring) of a device-side ring; apj_obs_fetch_ring reads any run of tickets back in one copy.
+// The reference's measurement cadence (fluctuations every 10 steps, jamming.cpp:211-216) then costs no host
+// round trip per measurement.
+int apj_obs_enqueue_ring(ApjObsScratch* o, const DevState& st, cudaStream_t s, long long* launches, int kind, const double* h_param, long long* ticket) {
+    if (kind < OBS_COM || kind > OBS_FLUCT) return -1;
+    if (kind == OBS_FLUCT && !h_param) return -1;
+    const long long tk = o->next_ticket;
+    if (int rc = enqueue2(o, st, s, launches, kind, kind == OBS_FLUCT ? h_param : nullptr, o->d_ring + 2 * (size_t)st.n_sys * (size_t)(tk % o->ring_cap))) return rc;
+    o->next_ticket = tk + 1;
+    if (ticket) *ticket = tk;
+    return 0;
+}
+int apj_obs_fetch_ring(ApjObsScratch* o, const DevState& st, cudaStream_t s, long long first, long long count, double* h_out) {
+    if (count < 0 || first < 0 || first + count > o->next_ticket || count > o->ring_cap || first < o->next_ticket - o->ring_cap) return -1;
+    const size_t row = 2 * (size_t)st.n_sys;
+    for (long long done = 0; done < count;) {          // at most two pieces (ring wrap)
+        const long long slot = (first + done) % o->ring_cap;
+        const long long n = std::min<long long>(count - done, o->ring_cap - slot);
+        if (cudaMemcpyAsync(h_out + row * done, o->d_ring + row * slot, sizeof(double) * row * n, cudaMemcpyDeviceToHost, s) != cudaSuccess) return APJ_E_CUDA_OBS;
+        done += n;
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess) return APJ_E_CUDA_OBS;
     return 0;
 }
 
@@ -279,7 +312,7 @@ int apj_obs_spatial(ApjObsScratch* o, const DevState& st, cudaStream_t s, long l
     cudaMemsetAsync(o->d_corr, 0, need * sizeof(double), s);
     const int bps = (st.N + OB - 1) / OB;
     const size_t smem = nb * sizeof(double);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(apj_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) apj_allow_max_smem(apj_spatial_kernel);
     apj_spatial_kernel<<<st.n_sys * bps, OB, smem, s>>>(st, bps, nc, np, 0, o->d_corr);
     if (launches) *launches += 1;
     std::vector<double> h(need);

@@ -671,30 +671,30 @@ void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nb
     // fixed grids: ~16 blocks of 128 threads per SM in total, shared out over the systems
     const int bps = std::max(1, std::min((st.cap + RB_BLOCK - 1) / RB_BLOCK, (148 * 16 + st.n_sys - 1) / st.n_sys));
     const int grid = st.n_sys * bps;
-    apj_bin_count_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
+    apj_bin_count_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps); apj_check_launch("apj_bin_count_kernel");
     if (st.slab) {
-        apj_slab_sync_kernel<<<1, 32, 0, l.stream>>>(st, 1);       // all migrants delivered
-        apj_absorb_kernel<<<std::max(1, std::min((st.mcap + RB_BLOCK - 1) / RB_BLOCK, 148 * 4)), RB_BLOCK, 0, l.stream>>>(st);
+        apj_slab_sync_kernel<<<1, 32, 0, l.stream>>>(st, 1); apj_check_launch("apj_slab_sync_kernel");       // all migrants delivered
+        apj_absorb_kernel<<<std::max(1, std::min((st.mcap + RB_BLOCK - 1) / RB_BLOCK, 148 * 4)), RB_BLOCK, 0, l.stream>>>(st); apj_check_launch("apj_absorb_kernel");
     }
     const int chunks = (max_nbox + SCAN_CHUNK - 1) / SCAN_CHUNK;       // == DevState::scan_chunks
     dim3 gc(chunks, st.n_sys);
-    apj_scan_chunk_sums_kernel<<<gc, SCAN_BLOCK, 0, l.stream>>>(st, chunks);
-    apj_scan_chunk_offsets_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st, chunks);
-    apj_scan_cells_kernel<<<gc, SCAN_BLOCK, 0, l.stream>>>(st, chunks);
-    apj_scatter_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
+    apj_scan_chunk_sums_kernel<<<gc, SCAN_BLOCK, 0, l.stream>>>(st, chunks); apj_check_launch("apj_scan_chunk_sums_kernel");
+    apj_scan_chunk_offsets_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st, chunks); apj_check_launch("apj_scan_chunk_offsets_kernel");
+    apj_scan_cells_kernel<<<gc, SCAN_BLOCK, 0, l.stream>>>(st, chunks); apj_check_launch("apj_scan_cells_kernel");
+    apj_scatter_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps); apj_check_launch("apj_scatter_kernel");
     dim3 gs(std::max(1, std::min((max_nbox + RB_BLOCK - 1) / RB_BLOCK, (148 * 16 + st.n_sys - 1) / st.n_sys)), st.n_sys);
-    apj_cell_sort_kernel<<<gs, RB_BLOCK, 0, l.stream>>>(st);
-    apj_reorder_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps);
+    apj_cell_sort_kernel<<<gs, RB_BLOCK, 0, l.stream>>>(st); apj_check_launch("apj_cell_sort_kernel");
+    apj_reorder_kernel<<<grid, RB_BLOCK, 0, l.stream>>>(st, bps); apj_check_launch("apj_reorder_kernel");
     if (st.slab) {
-        apj_push_ghosts_kernel<<<std::max(1, std::min((st.gcap + RB_BLOCK - 1) / RB_BLOCK, 148 * 4)), RB_BLOCK, 0, l.stream>>>(st);
-        apj_slab_sync_kernel<<<1, 32, 0, l.stream>>>(st, 2);       // ghost columns in place on every rank
+        apj_push_ghosts_kernel<<<std::max(1, std::min((st.gcap + RB_BLOCK - 1) / RB_BLOCK, 148 * 4)), RB_BLOCK, 0, l.stream>>>(st); apj_check_launch("apj_push_ghosts_kernel");
+        apj_slab_sync_kernel<<<1, 32, 0, l.stream>>>(st, 2); apj_check_launch("apj_slab_sync_kernel");       // ghost columns in place on every rank
     }
-    apj_make_tiles_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st);
-    apj_fill_tiles_kernel<<<dim3((st.maxblk + RB_BLOCK - 1) / RB_BLOCK, st.n_sys), RB_BLOCK, 0, l.stream>>>(st);
+    apj_make_tiles_kernel<<<st.n_sys, SCAN_BLOCK, 0, l.stream>>>(st); apj_check_launch("apj_make_tiles_kernel");
+    apj_fill_tiles_kernel<<<dim3((st.maxblk + RB_BLOCK - 1) / RB_BLOCK, st.n_sys), RB_BLOCK, 0, l.stream>>>(st); apj_check_launch("apj_fill_tiles_kernel");
     int lgG = 0;
     while ((1 << lgG) < st.G) lgG++;
-    apj_verlet_build_kernel<<<st.n_sys * st.maxblk, st.ppb, apj_build_smem_bytes(st), l.stream>>>(st, lgG);
-    apj_finish_rebuild_kernel<<<(st.n_sys + 63) / 64, 64, 0, l.stream>>>(st);
+    apj_verlet_build_kernel<<<st.n_sys * st.maxblk, st.ppb, apj_build_smem_bytes(st), l.stream>>>(st, lgG); apj_check_launch("apj_verlet_build_kernel");
+    apj_finish_rebuild_kernel<<<(st.n_sys + 63) / 64, 64, 0, l.stream>>>(st); apj_check_launch("apj_finish_rebuild_kernel");
     if (l.launch_counter) (*l.launch_counter) += apj_rebuild_chain_launches(st);
 }
 int apj_rebuild_chain_launches(const DevState& st) { return st.slab ? 15 : 11; }
@@ -704,7 +704,6 @@ int apj_scan_chunk_cells() { return SCAN_CHUNK; }
 // dynamic shared memory of the list build: the {x,y} tile + the staging array of 16-bit hits, [S][particles of the block]
 size_t apj_build_smem_bytes(const DevState& st) { return (size_t)(st.tile_cap + 1) * 16 + (size_t)st.S * st.ppb * 2; }
 int apj_configure_rebuild(const DevState& st) {
-    const int bytes = (int)apj_build_smem_bytes(st);
-    if (bytes <= 48 * 1024) return 0;
-    return cudaFuncSetAttribute(apj_verlet_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : -1;
+    (void)st;
+    return apj_allow_max_smem(apj_verlet_build_kernel) ? 0 : -1;
 }

@@ -118,29 +118,79 @@ __device__ __forceinline__ void word_terms(PairAcc& a, const double2 me, const d
     if (d21 < rn2) pair_force(a, Ri, dx1, dy1, d21, at1, dCS, dRR);
 }
 
-#ifndef APJ_QREG
-#define APJ_QREG 3
-#endif
-constexpr int QREG = APJ_QREG;   // list quads (4 words = 8 entries each) a thread keeps in registers
+constexpr int QREG = 2;   // list quads (4 words = 8 entries each) a thread holds in registers at any time
 
-// nw = list words of this lane; q[] = its first QREG quads (loaded before the tile landed);
-// gq = the lane's quad column in global memory (stride TB) for the rare longer lists
+// one quad of list words (bounds: the lane's list has nw words, this quad starts at word w0)
+template <bool WRAP>
+__device__ __forceinline__ void quad_terms(PairAcc& acc, const uint4 qd, const int w0, const int nw, const double2 me, const double Ri,
+                                           const unsigned sXY, const unsigned dCS, const unsigned dRR, const double L, const double Lh,
+                                           const double rn2) {
+    word_terms<WRAP>(acc, me, Ri, qd.x, sXY, dCS, dRR, L, Lh, rn2);
+    if (w0 + 1 < nw) word_terms<WRAP>(acc, me, Ri, qd.y, sXY, dCS, dRR, L, Lh, rn2);
+    if (w0 + 2 < nw) word_terms<WRAP>(acc, me, Ri, qd.z, sXY, dCS, dRR, L, Lh, rn2);
+    if (w0 + 3 < nw) word_terms<WRAP>(acc, me, Ri, qd.w, sXY, dCS, dRR, L, Lh, rn2);
+}
+
+// nw = list words of this lane; q[] = its first two quads (requested before the tile landed); gq = the lane's quad
+// column in global memory (stride TB). Two quads rotate through the registers: while one is swept, the one after
+// the next is already on its way into the registers of the one just finished (a quad is ~200 instructions of
+// sweep, far longer than the load), so lists of any length run at the same pace on 8 list registers.
 template <int TB, bool WRAP>
 __device__ __forceinline__ void sweep(PairAcc& acc, const int nw, const uint4 (&q)[QREG], const uint4* __restrict__ gq,
                                       const double2 me, const double Ri, const unsigned sXY, const unsigned dCS,
                                       const unsigned dRR, const double L, const double Lh, const double rn2) {
-#pragma unroll
-    for (int j = 0; j < QREG; j++) {
-        if (4 * j < nw) {
-            word_terms<WRAP>(acc, me, Ri, q[j].x, sXY, dCS, dRR, L, Lh, rn2);
-            if (4 * j + 1 < nw) word_terms<WRAP>(acc, me, Ri, q[j].y, sXY, dCS, dRR, L, Lh, rn2);
-            if (4 * j + 2 < nw) word_terms<WRAP>(acc, me, Ri, q[j].z, sXY, dCS, dRR, L, Lh, rn2);
-            if (4 * j + 3 < nw) word_terms<WRAP>(acc, me, Ri, q[j].w, sXY, dCS, dRR, L, Lh, rn2);
+    uint4 qa = q[0], qb = q[1];
+    for (int w0 = 0; w0 < nw; w0 += 8) {
+        quad_terms<WRAP>(acc, qa, w0, nw, me, Ri, sXY, dCS, dRR, L, Lh, rn2);
+        if (w0 + 8 < nw) qa = __ldg(gq + (size_t)((w0 >> 2) + 2) * TB);
+        if (w0 + 4 < nw) {
+            quad_terms<WRAP>(acc, qb, w0 + 4, nw, me, Ri, sXY, dCS, dRR, L, Lh, rn2);
+            if (w0 + 12 < nw) qb = __ldg(gq + (size_t)((w0 >> 2) + 3) * TB);
         }
     }
-    for (int k = 4 * QREG; k < nw; k++) {             // rare: more than 8*QREG entries on this lane
-        const unsigned word = __ldg(reinterpret_cast<const unsigned*>(gq + (size_t)(k >> 2) * TB) + (k & 3));
-        word_terms<WRAP>(acc, me, Ri, word, sXY, dCS, dRR, L, Lh, rn2);
+}
+
+// phi = atan2(y_new, x_new) + CTnoise * randuni()   (jamming.cpp:667), then Cell::update: periodicAngles (single
+// wrap, Cell.h:160-166), cosp = cos(phi), sinp = sin(phi). (ax, ay) = alignment sum, nz = the noise term. phi itself
+// is only formed when the caller wants it (observables / downloads) or the fast form does not apply.
+__device__ __forceinline__ void apj_new_orientation(const double ax, const double ay, const double nz, const bool want_phi,
+                                                    double& phi, double& cs, double& sn) {
+    phi = 0.0;
+    const double r2 = ax * ax + ay * ay;
+#ifndef APJ_EXACT_TRIG
+    const double anz = fabs(nz);
+    const bool fast = anz >= 1e-7 && anz <= 3.0 && r2 > 1e-200 && r2 < 1e200;
+#else
+    const bool fast = false;
+#endif
+    if (fast) {
+        // cos and sin of theta + eta by the angle-addition identity, theta = atan2(ay, ax) never formed:
+        // (cos theta, sin theta) = (ax, ay) / r, one rsqrt and one sincos(eta) instead of atan2 + sincos.
+        // Both forms are within ~1e-15 of the exact value (measured 1.2e-15 apart over 1.2e7 samples),
+        // far inside the 1e-12 gate. The reference's wrap uses truncated constants: when theta + eta
+        // leaves [-PI, PI) it shifts phi by PI2 = 6.28318531, i.e. rotates (cos, sin) by PI2 - 2 pi.
+        // Whether it wraps follows from the signs (theta = atan2(ay, ax) carries the sign BIT of ay, so
+        // ay = -0.0 with ax < 0 is theta = -pi): for eta > 0 (theta >= 0 required) phi >= PI iff
+        // sin(phi) < 0, or cos(phi) < 0 and sin(phi) <= sin(PI); mirrored for eta < 0.
+        double sn_n, cn_n;
+        sincos(nz, &sn_n, &cn_n);
+        const double inv = rsqrt(r2);
+        const double c0 = ax * inv, s0 = ay * inv;
+        cs = c0 * cn_n - s0 * sn_n;
+        sn = s0 * cn_n + c0 * sn_n;
+        constexpr double SIN_PI = 3.5897930298416118e-09;    // sin(3.14159265) evaluated on the double constant
+        constexpr double DPI2 = 2.8204138795420667e-09;      // 6.28318531 (as a double) - 2 pi
+        if (nz > 0.0 && !signbit(ay) && (sn < 0.0 || (cs < 0.0 && sn <= SIN_PI))) {
+            const double c = cs; cs = c + sn * DPI2; sn = sn - c * DPI2;      // phi -= PI2
+        } else if (nz < 0.0 && signbit(ay) && (sn > 0.0 || (cs < 0.0 && sn > -SIN_PI))) {
+            const double c = cs; cs = c - sn * DPI2; sn = sn + c * DPI2;      // phi += PI2
+        }
+    }
+    if (!fast || want_phi) {
+        phi = atan2(ay, ax) + nz;
+        if (phi >= APJ_PI) phi -= APJ_PI2;
+        else if (phi < -APJ_PI) phi += APJ_PI2;
+        if (!fast) sincos(phi, &sn, &cs);
     }
 }
 
@@ -185,10 +235,7 @@ __device__ __forceinline__ void apj_commit(SysCtl* __restrict__ ctl, const DevSt
 #define APJ_BLOCKS_224 5   // 56 registers per thread: 35 warps per SM
 #endif
 constexpr int apj_blocks_for(int tb) { return tb == 256 ? APJ_BLOCKS_256 : (tb == 224 ? APJ_BLOCKS_224 : (tb == 192 ? APJ_BLOCKS_192 : APJ_BLOCKS_128)); }
-// PERSIST (one large system, split tail): the grid is one wave of resident blocks and each block walks the
-// tiles blk, blk + gridDim.x, ... The next tile's descriptor is fetched one tile ahead, so a tile starts
-// with its TMA copies instead of a descriptor round trip, and no block launch sits between two tiles.
-template <int TB, int G, bool INJECT, bool SLAB, bool SPLIT, bool PERSIST>
+template <int TB, int G, bool INJECT, bool SLAB, bool SPLIT>
 __global__ void __launch_bounds__(TB, apj_blocks_for(TB))
 apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const int always_full) {
     constexpr int PPB = TB / G;                        // particles per block
@@ -198,13 +245,12 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ double4 s_red[EWARPS];
 
-    static_assert(!PERSIST || (SPLIT && G == 1), "the persistent form is the split-tail kernel of one large system");
-    const int sys = (PERSIST || st.n_sys == 1) ? 0 : blockIdx.x / st.maxblk;
-    int blk = PERSIST ? (int)blockIdx.x : (int)(blockIdx.x - sys * st.maxblk);
+    const int sys = st.n_sys == 1 ? 0 : blockIdx.x / st.maxblk;
+    const int blk = (int)(blockIdx.x - sys * st.maxblk);
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    long long bg = (long long)sys * st.maxblk + blk;
+    const long long bg = (long long)sys * st.maxblk + blk;
     int desc_word = 0;                                 // fetched alongside ctl: one round trip, not two
-    if (t < 16) desc_word = __ldg(reinterpret_cast<const int*>(st.tiles + bg) + t);
+    if (t < 16) desc_word = apj_ldg_l2keep(reinterpret_cast<const int*>(st.tiles + bg) + t);
     // Cross-block software prefetch. A step streams ~3 GB through the 126 MB L2, so nothing a block needs
     // is still cached from the previous step and its head would be two dependent HBM round trips
     // (descriptor, then tile + lists). Blocks are dispatched in index order, so each block asks L2 for
@@ -213,7 +259,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     // list quads and per-particle arrays, and touches the descriptor of block blk + 2 PF.
     constexpr int PF = APJ_PF_DIST;
     int fdesc = 0;
-    if (PF > 0 && !PERSIST && wid == TB / 32 - 1) {
+    if (PF > 0 && wid == TB / 32 - 1) {
         if (lane < 16 && blk + PF < st.maxblk) fdesc = __ldg(reinterpret_cast<const int*>(st.tiles + bg + PF) + lane);
         if (lane == 16 && blk + 2 * PF < st.maxblk) apj_prefetch_l2(st.tiles + bg + 2 * PF);
     }
@@ -224,21 +270,6 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
 
     const int cur = ctl->cur, gen = ctl->gen;
     __shared__ int s_kcls;                             // distance classes this launch sweeps (0..kcls): uniform, derived by one thread
-    int desc_next = 0;                                 // PERSIST: descriptor of this block's next tile, one tile ahead
-    if (PERSIST && t < 16 && blk + (int)gridDim.x < nblk) desc_next = __ldg(reinterpret_cast<const int*>(st.tiles + bg + gridDim.x) + t);
-    unsigned phase = 0;                                // parity of the tile mbarrier (flips per tile)
-    bool first = true;
-#ifndef APJ_PERSIST_STAGGER_NS
-#define APJ_PERSIST_STAGGER_NS 2300
-#endif
-    if (PERSIST && APJ_PERSIST_STAGGER_NS > 0) {
-        // The resident blocks of an SM would otherwise start together and stay in step for most of the launch
-        // (tiles take nearly the same time), all waiting for their tiles at once and all computing at once.
-        // Start them a fraction of a tile time apart, so that one block's tile wait overlaps the others' sweeps.
-        const unsigned slot = blockIdx.x / (unsigned)st.persist_sms;
-        if (slot) __nanosleep(slot * APJ_PERSIST_STAGGER_NS);
-    }
-
     // tile: slot 0 is the sentinel, slots 1.. are the concatenated pieces; three arrays of 16-byte
     // records {x,y}, {cos,sin}, {R,1/R}, each tile_cap+1 records long
     double2* __restrict__ sXYp = reinterpret_cast<double2*>(smem_raw);
@@ -246,14 +277,13 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     double2* __restrict__ sRRp = sCSp + (st.tile_cap + 1);
     double4* __restrict__ sAcc = reinterpret_cast<double4*>(sRRp + (st.tile_cap + 1));   // G > 1 only
 
-  for (;;) {   // one pass per tile (exactly one unless PERSIST)
     // Stage the tile: <= 6 pieces x 3 arrays, one TMA bulk copy each. Warp 0 holds the descriptor in
     // registers (lanes 0..15); lane 3*p + a issues the copy of piece p of array a, so the <= 18 copies
     // leave in one instruction instead of a serial loop on one thread, and they leave BEFORE the block
     // barrier that publishes the descriptor to the other warps.
     if (wid == 0) {
         if (lane < 16) reinterpret_cast<int*>(&sd)[lane] = desc_word;
-        if (lane == 0 && first) { apj_mbar_init(&s_bar, 1); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+        if (lane == 0) { apj_mbar_init(&s_bar, 1); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
         __syncwarp();
         const int np = __shfl_sync(0xffffffffu, desc_word, 3) & 0xff;
         const int mp = lane / 3, arr = lane - mp * 3;
@@ -275,7 +305,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
             apj_bulk_g2s(dst + my_off, src + my_start, (unsigned)my_len * 16u, &s_bar);
         }
     }
-    if (t == 32 % TB && first) { sXYp[0] = make_double2(1e300, 1e300); s_kcls = apj_sweep_class(ctl, st); }
+    if (t == 32 % TB) { sXYp[0] = make_double2(1e300, 1e300); s_kcls = apj_sweep_class(ctl, st); }
     __syncthreads();
     const int kcls = s_kcls;
 
@@ -292,10 +322,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     const uint4* __restrict__ gq = reinterpret_cast<const uint4*>(st.list32) + bg * (long long)st.max_quads * TB + t;
     uint4 q[QREG];                                     // the first two quads do not wait for cnt (stale words are never swept)
 #pragma unroll
-    for (int j = 0; j < QREG; j++) {
-        q[j] = make_uint4(0u, 0u, 0u, 0u);
-        if (j < 2 || 4 * j < nw) q[j] = __ldg(gq + (size_t)j * TB);
-    }
+    for (int j = 0; j < QREG; j++) q[j] = (j < st.max_quads) ? __ldg(gq + (size_t)j * TB) : make_uint4(0u, 0u, 0u, 0u);
     const bool active = t < sd.n;                      // epilogue mapping: thread t <-> particle t
     const long long g = (long long)sd.g0 + (active ? t : 0);
     double2 xo = make_double2(0.0, 0.0), xr = xo;
@@ -315,7 +342,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         }
     }
 
-    if (PF > 0 && !PERSIST && wid == TB / 32 - 1 && blk + PF < nblk) {   // this warp's own loads are in flight: ask L2 for block blk + PF
+    if (PF > 0 && wid == TB / 32 - 1 && blk + PF < nblk) {   // this warp's own loads are in flight: ask L2 for block blk + PF
         const int fnp = __shfl_sync(0xffffffffu, fdesc, 3) & 0xff;
         const int fg0 = __shfl_sync(0xffffffffu, fdesc, 0), fn = __shfl_sync(0xffffffffu, fdesc, 1);
         const int mp = lane / 3, arr = lane - mp * 3;
@@ -338,8 +365,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     }
 
     unsigned sXY = apj_smem_addr(sXYp);
-    apj_mbar_wait(&s_bar, phase, sXY);
-    phase ^= 1u;
+    apj_mbar_wait(&s_bar, 0u, sXY);
     const unsigned dCS = (unsigned)(st.tile_cap + 1) * 16u, dRR = 2u * dCS;
 
     // ---- neighborInteractions ----
@@ -385,43 +411,8 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         //      periodicAngles (single wrap, Cell.h:160-166), cosp = cos(phi), sinp = sin(phi) ----
         const double nz = ctl->CTnoise * u;
         const bool want_phi = always_full || step + 1 == ctl->target;   // phi itself is only read by observables / downloads
-        double phi = 0.0, sn, cs;
-        const double r2 = ax * ax + ay * ay;
-#ifndef APJ_EXACT_TRIG
-        const double anz = fabs(nz);
-        const bool fast = anz >= 1e-7 && anz <= 3.0 && r2 > 1e-200 && r2 < 1e200;
-#else
-        const bool fast = false;
-#endif
-        if (fast) {
-            // cos and sin of theta + eta by the angle-addition identity, theta = atan2(ay, ax) never formed:
-            // (cos theta, sin theta) = (ax, ay) / r, one rsqrt and one sincos(eta) instead of atan2 + sincos.
-            // Both forms are within ~1e-15 of the exact value (measured 1.2e-15 apart over 1.2e7 samples),
-            // far inside the 1e-12 gate. The reference's wrap uses truncated constants: when theta + eta
-            // leaves [-PI, PI) it shifts phi by PI2 = 6.28318531, i.e. rotates (cos, sin) by PI2 - 2 pi.
-            // Whether it wraps follows from the signs (theta = atan2(ay, ax) carries the sign BIT of ay, so
-            // ay = -0.0 with ax < 0 is theta = -pi): for eta > 0 (theta >= 0 required) phi >= PI iff
-            // sin(phi) < 0, or cos(phi) < 0 and sin(phi) <= sin(PI); mirrored for eta < 0.
-            double sn_n, cn_n;
-            sincos(nz, &sn_n, &cn_n);
-            const double inv = rsqrt(r2);
-            const double c0 = ax * inv, s0 = ay * inv;
-            cs = c0 * cn_n - s0 * sn_n;
-            sn = s0 * cn_n + c0 * sn_n;
-            constexpr double SIN_PI = 3.5897930298416118e-09;    // sin(3.14159265) evaluated on the double constant
-            constexpr double DPI2 = 2.8204138795420667e-09;      // 6.28318531 (as a double) - 2 pi
-            if (nz > 0.0 && !signbit(ay) && (sn < 0.0 || (cs < 0.0 && sn <= SIN_PI))) {
-                const double c = cs; cs = c + sn * DPI2; sn = sn - c * DPI2;      // phi -= PI2
-            } else if (nz < 0.0 && signbit(ay) && (sn > 0.0 || (cs < 0.0 && sn > -SIN_PI))) {
-                const double c = cs; cs = c - sn * DPI2; sn = sn + c * DPI2;      // phi += PI2
-            }
-        }
-        if (!fast || want_phi) {
-            phi = atan2(ay, ax) + nz;
-            if (phi >= APJ_PI) phi -= APJ_PI2;
-            else if (phi < -APJ_PI) phi += APJ_PI2;
-            if (!fast) sincos(phi, &sn, &cs);
-        }
+        double phi, sn, cs;
+        apj_new_orientation(ax, ay, nz, want_phi, phi, cs, sn);
         double CF = ctl->CFself;
         if (ctl->ramp_len > 0) {                      // relax() ramp (jamming.cpp:518)
             const long long t_ = step - ctl->ramp_t0;
@@ -469,7 +460,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     if (EWARPS > 1) {
         if (lane == 0) s_red[wid] = make_double4(sum_x, sum_y, top1, top2);
         __syncthreads();       // all EWARPS == all warps of the block when EWARPS > 1 (G == 1 or 2)
-        if (!PERSIST && wid != 0) return;
+        if (wid != 0) return;
         if (wid == 0) {
 #pragma unroll
             for (int w = 1; w < EWARPS; w++) {
@@ -478,22 +469,6 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
                 apj_top2_merge(top1, top2, b.z, b.w);
             }
         }
-    }
-    if (PERSIST) {
-        // the barrier above also says that every warp is done with this tile's shared memory. Warp 0
-        // leaves the block's partial; then everybody moves to the block's next tile, whose descriptor
-        // arrived while this one was being computed.
-        if (wid == 0) {
-            if (SLAB && (sd.info & (APJ_INFO_PUSH_LEFT | APJ_INFO_PUSH_RIGHT))) { __syncwarp(); __threadfence_system(); }
-            if (lane == 0) st.partials[bg] = make_double4(sum_x, sum_y, top1, top2);
-        }
-        blk += (int)gridDim.x;
-        if (blk >= nblk) return;
-        bg = blk;
-        desc_word = desc_next;
-        if (t < 16 && blk + (int)gridDim.x < nblk) desc_next = __ldg(reinterpret_cast<const int*>(st.tiles + bg + gridDim.x) + t);
-        first = false;
-        continue;
     }
     // warp 0 only from here. Two-level, fixed-order reduction of the per-block partials: the last
     // block of each group of 32 folds its group, the last group to finish folds the groups and
@@ -591,7 +566,290 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         apj_commit(ctl, st, a, kcls);
     }
     return;
-  }   // tile loop
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pipelined persistent form of the step (one large system, one lane per particle, split tail).
+//
+// The grid is ONE wave of resident blocks; block b walks the tiles b, b + grid, b + 2 grid, ... A block of the
+// classic kernel above spends ~40 % of its life in its head -- descriptor round trip, then tile + lists + per-
+// particle arrays, two dependent trips to HBM -- with nothing to compute. Here the trips of tile i+1 run under
+// the epilogue of tile i:
+//   * the tile buffer is only read by the neighbour sweep. The LAST warp of the block to finish its sweep
+//     (shared-memory arrival counter, no block barrier) issues the TMA copies of the next tile straight into
+//     the buffer, plus a 64-byte bulk copy of the descriptor of the tile after that, all completing on the one
+//     mbarrier whose phase the next sweep waits for;
+//   * the own particle's {cos,sin}, {R,1/R} are the last reads of the buffer; x_old / x_real are read from global
+//     memory after the sweep -- L2 hits, because the thread asked L2 for them a tile earlier -- while Philox runs;
+//   * the first list quad of the next tile travels to the thread's shared-memory slot with cp.async, list
+//     lengths and ids are requested before the epilogue starts.
+// Warps never wait for each other inside the loop: a warp waits for "tile landed", sweeps, signals, updates its
+// particles, moves on. Per-lane running sums of x_real (shared memory) and per-warp running top-2 displacements
+// are folded once, in a fixed order, when the block has run out of tiles: one partial per BLOCK.
+// Same arithmetic in the same order per particle as the classic kernel: positions are bit-identical to it.
+#ifndef APJ_PIPE_BLOCKS
+#define APJ_PIPE_BLOCKS 4
+#endif
+struct PipeSmem {
+    TileDesc sd[3];                  // descriptors of tiles i-1 / i / i+1 (slot = visit number % 3)
+    unsigned long long full;         // mbarrier: tile (and the next descriptor) landed
+    unsigned done;                   // warps that finished sweeping the current tile
+    int kcls, pushed;
+    double2 top[APJ_TB_MAX / 32];    // per warp: running top-2 displacement^2
+    double4 red[APJ_TB_MAX / 32];
+};
+
+// whole warp: TMA copies of the tile described by d (shared memory) + the descriptor `next_src` (may be null)
+__device__ __forceinline__ void pipe_issue(const DevState& st, const TileDesc* d, const int cur, const int gen, double2* sXYp, double2* sCSp,
+                                           double2* sRRp, unsigned long long* bar, const TileDesc* next_src, TileDesc* next_dst) {
+    const int lane = threadIdx.x & 31;
+    const int np = d->info & 0xff;
+    const int mp = lane / 3, arr = lane - mp * 3;
+    int off = 1, my_off = 1, my_len = 0, my_start = 0;
+#pragma unroll
+    for (int q = 0; q < APJ_MAX_PIECES; q++) {
+        if (q < np) {
+            const int len = d->plen[q];
+            if (q == mp) { my_off = off; my_len = len; my_start = d->pstart[q]; }
+            off += len;
+        }
+    }
+    if (lane == 0) apj_mbar_expect_tx(bar, (unsigned)(off - 1) * 48u + (next_src ? (unsigned)sizeof(TileDesc) : 0u));
+    __syncwarp();
+    if (mp < np && my_len > 0) {
+        const double2* src = arr == 0 ? st.XY[cur] : (arr == 1 ? st.CS[cur] : st.RR[gen]);
+        double2* dst = arr == 0 ? sXYp : (arr == 1 ? sCSp : sRRp);
+        apj_bulk_g2s(dst + my_off, src + my_start, (unsigned)my_len * 16u, bar);
+    }
+    if (lane == 31 && next_src) apj_bulk_g2s(next_dst, next_src, (unsigned)sizeof(TileDesc), bar);
+}
+
+template <int TB, bool INJECT, bool SLAB>
+__global__ void __launch_bounds__(TB, APJ_PIPE_BLOCKS)
+apj_step_pipe_kernel(const DevState st, const double* __restrict__ noise_by_id, const int always_full) {
+    constexpr int NW = TB / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(128) PipeSmem sm;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    SysCtl* __restrict__ ctl = st.ctl;
+    const int nblk = ctl->nblk;
+    const long long step = ctl->step;
+    int tile = blockIdx.x;
+    if (tile >= nblk || ctl->stale || step >= ctl->target) return;   // uniform over the block
+    const int cur = ctl->cur, gen = ctl->gen;
+    const int stride = gridDim.x;
+
+    // tile: slot 0 is the sentinel, slots 1.. are the concatenated pieces; three arrays of 16-byte records, then the
+    // per-thread running sums of x_real
+    double2* __restrict__ sXYp = reinterpret_cast<double2*>(smem_raw);
+    double2* __restrict__ sCSp = sXYp + (st.tile_cap + 1);
+    double2* __restrict__ sRRp = sCSp + (st.tile_cap + 1);
+    double2* __restrict__ sSum = sRRp + (st.tile_cap + 1);
+    uint4* __restrict__ sQ0 = reinterpret_cast<uint4*>(sSum + TB);      // per thread: first list quad of the tile about to be swept
+
+    if (t < 16) reinterpret_cast<int*>(&sm.sd[0])[t] = __ldg(reinterpret_cast<const int*>(st.tiles + tile) + t);
+    if (t == 32) {
+        apj_mbar_init(&sm.full, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        sm.done = 0u; sm.pushed = 0;
+        sXYp[0] = make_double2(1e300, 1e300);
+        sm.kcls = apj_sweep_class(ctl, st);
+    }
+    sSum[t] = make_double2(0.0, 0.0);
+    if (lane == 0) sm.top[wid] = make_double2(0.0, 0.0);
+    __syncthreads();
+    if (wid == 0)
+        pipe_issue(st, &sm.sd[0], cur, gen, sXYp, sCSp, sRRp, &sm.full, tile + stride < nblk ? st.tiles + tile + stride : nullptr, &sm.sd[1]);
+    const int kcls = sm.kcls;
+    const double L = ctl->L, Lh = ctl->Lover2;
+    const double rn2 = st.rn2;
+    const unsigned dCS = (unsigned)(st.tile_cap + 1) * 16u, dRR = 2u * dCS;
+
+    // What a tile needs from global memory besides the tile itself is requested one tile ahead WITHOUT holding
+    // registers across the epilogue: the thread's first list quad goes to its own shared-memory slot with
+    // cp.async (the second one is loaded when the sweep starts and is consumed a quad later), its x_old / x_real
+    // records are pulled into L2 so that the loads after the sweep are L2 hits that Philox covers.
+    unsigned cntk_raw;                                 // list lengths of the next tile: used (shifted) only after the tile wait
+    int id;
+    auto load_early = [&](const TileDesc& d, const int tl) {
+        const bool mine = t < d.n;
+        const long long g = (long long)d.g0 + (mine ? t : 0);
+        const uint4* gq = reinterpret_cast<const uint4*>(st.list32) + (long long)tl * st.max_quads * TB + t;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(apj_smem_addr(sQ0 + t)), "l"(gq) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        apj_prefetch_l2(st.XO[gen] + g);
+        apj_prefetch_l2(st.XR[cur] + g);
+        cntk_raw = mine ? st.cntk[g] : 0u;
+        id = st.ID[gen][g];
+    };
+    load_early(sm.sd[0], tile);
+
+    int k = 0;                                         // descriptor slot of the current tile
+    unsigned phase = 0;
+    for (;;) {
+        const TileDesc& d = sm.sd[k];
+        unsigned sXY = apj_smem_addr(sXYp);
+        apj_mbar_wait(&sm.full, phase, sXY);
+        phase ^= 1u;
+        const bool active = t < d.n;
+        const long long g = (long long)d.g0 + (active ? t : 0);
+        const bool wraps = (d.info & APJ_INFO_WRAPS) != 0;
+        const int my_id = id;
+        const int nent = (int)((cntk_raw >> (8 * kcls)) & 0xffu);
+        // the tile after this one: ask L2 for its pieces now, so that the refill issued at the end of this sweep is a
+        // run of L2 hits (its descriptor arrived with this tile)
+        if (wid == NW - 1 && tile + stride < nblk) {
+            const TileDesc& dn = sm.sd[k == 2 ? 0 : k + 1];
+            const int mp = lane / 3, arr = lane - mp * 3;
+            if (mp < (dn.info & 0xff) && mp < APJ_MAX_PIECES) {
+                const double2* src = arr == 0 ? st.XY[cur] : (arr == 1 ? st.CS[cur] : st.RR[gen]);
+                apj_bulk_prefetch_l2(src + dn.pstart[mp], (unsigned)dn.plen[mp] * 16u);
+            }
+        }
+
+        // ---- neighborInteractions ----
+        PairAcc acc = {0.0, 0.0, 0.0, 0.0};
+        const unsigned own = (unsigned)(d.own_slot + (active ? t : 0)) * 16u;
+        const double2 me = lds_f64x2(sXY + own);
+        double2 mcs, mrr;
+        {
+            const double Ri = lds_f64(sXY + dRR + own);
+            const int nw = (nent + 1) >> 1;
+            const uint4* gq = reinterpret_cast<const uint4*>(st.list32) + (long long)tile * st.max_quads * TB + t;
+            uint4 q[QREG];
+            q[1] = st.max_quads > 1 ? __ldg(gq + TB) : make_uint4(0u, 0u, 0u, 0u);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            q[0] = sQ0[t];
+            if (wraps) sweep<TB, true>(acc, nw, q, gq, me, Ri, sXY, dCS, dRR, L, Lh, rn2);
+            else sweep<TB, false>(acc, nw, q, gq, me, Ri, sXY, dCS, dRR, L, Lh, rn2);
+            // own {cos,sin}, {R,1/R}: the last reads of the tile buffer
+            mcs = lds_f64x2(sXY + dCS + own);
+            mrr = lds_f64x2(sXY + dRR + own);
+        }
+
+        // ---- hand the tile buffer back: the last warp to get here refills it with the block's next tile ----
+        const int nxt = tile + stride;
+        {
+            unsigned last = 0;
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                last = (atomicAdd(&sm.done, 1u) == (unsigned)NW - 1u) ? 1u : 0u;
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                if (lane == 0) sm.done = 0u;
+                if (nxt < nblk) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const int k1 = k == 2 ? 0 : k + 1, k2 = k1 == 2 ? 0 : k1 + 1;
+                    pipe_issue(st, &sm.sd[k1], cur, gen, sXYp, sCSp, sRRp, &sm.full,
+                               nxt + stride < nblk ? st.tiles + nxt + stride : nullptr, &sm.sd[k2]);
+                }
+            }
+        }
+        // ---- own-particle inputs of the epilogue: from global memory (the tile buffer is being overwritten) ----
+        double2 xo = make_double2(0.0, 0.0), xr = xo;
+        if (active) { xo = st.XO[gen][g]; xr = st.XR[cur][g]; }
+        // what the next tile needs from global memory is requested now, under the epilogue
+        const int info = d.info;
+        if (nxt < nblk) load_early(sm.sd[k == 2 ? 0 : k + 1], nxt);
+
+        double sum_x = 0.0, sum_y = 0.0, top1 = 0.0;
+        if (active) {
+            // randuni() of this step (jamming.cpp:667)
+            double u;
+            if (INJECT) {
+                u = noise_by_id[my_id];
+            } else {
+                const unsigned w = apj_philox_word0((unsigned)my_id, (unsigned)step, (unsigned)(step >> 32), 0u,
+                                                    (unsigned)st.seed, (unsigned)(st.seed >> 32));
+                u = apj_u32_to_randuni(w);
+            }
+            const double Ri = mrr.x;
+            double Fx = acc.Fx, Fy = acc.Fy, ax = acc.ax, ay = acc.ay;
+            if (!ctl->no_self_once) { ax += mcs.x; ay += mcs.y; }  // self term: Cell::update left x_new = cosp (Cell.h:102-103)
+            {   // newSkinList: displacement since the last rebuild, COM drift removed
+                const double ddx = apj_delta_norm(((me.x - xo.x) - ctl->COM[0]) + ctl->COM_old[0], L, Lh);
+                const double ddy = apj_delta_norm(((me.y - xo.y) - ctl->COM[1]) + ctl->COM_old[1], L, Lh);
+                top1 = apj_d2(ddx, ddy);
+            }
+            const double nz = ctl->CTnoise * u;
+            const bool want_phi = always_full || step + 1 == ctl->target;
+            double phi, sn, cs;
+            apj_new_orientation(ax, ay, nz, want_phi, phi, cs, sn);
+            double CF = ctl->CFself;
+            if (ctl->ramp_len > 0) {                      // relax() ramp (jamming.cpp:518)
+                const long long t_ = step - ctl->ramp_t0;
+                if (t_ < ctl->ramp_len) CF = CF - (double)(ctl->ramp_len - t_) * CF / (double)ctl->ramp_len;
+            }
+            Fx += cs * CF * Ri;
+            Fy += sn * CF * Ri;
+            const double vx = Fx * mrr.y, vy = Fy * mrr.y;   // Rinv = 1/R stored at upload (jamming.cpp:298)
+            const double dx = vx * st.dt, dy = vy * st.dt;
+            double x = me.x + dx, y = me.y + dy;
+            const double xrn = xr.x + dx, yrn = xr.y + dy;
+            if (x >= Lh) x -= L; else if (x < -Lh) x += L;   // Cell::PBC, single wrap (Cell.h:168-175)
+            if (y >= Lh) y -= L; else if (y < -Lh) y += L;
+            st.XY[cur ^ 1][g] = make_double2(x, y);
+            st.CS[cur ^ 1][g] = make_double2(cs, sn);
+            st.XR[cur ^ 1][g] = make_double2(xrn, yrn);
+            if (SLAB) {   // halo exchange fused into the epilogue (see the classic kernel)
+                if (info & APJ_INFO_PUSH_LEFT) {
+                    const long long pg = (long long)st.cap + st.gcap + g;
+                    apj_peer(st, st.left, st.XY[cur ^ 1])[pg] = make_double2(x, y);
+                    apj_peer(st, st.left, st.CS[cur ^ 1])[pg] = make_double2(cs, sn);
+                }
+                if (info & APJ_INFO_PUSH_RIGHT) {
+                    const long long pg = (long long)st.cap + (g - ctl->last_col_start);
+                    apj_peer(st, st.right, st.XY[cur ^ 1])[pg] = make_double2(x, y);
+                    apj_peer(st, st.right, st.CS[cur ^ 1])[pg] = make_double2(cs, sn);
+                }
+            }
+            if (want_phi) {   // fields only observables read
+                st.V[gen][g] = make_double2(vx, vy);
+                st.PHI[gen][g] = phi;
+            }
+            sum_x = xrn; sum_y = yrn;
+        }
+        // running reductions of the block: x_real per lane, top-2 displacement^2 per warp
+        {
+            const double2 a = sSum[t];
+            sSum[t] = make_double2(a.x + sum_x, a.y + sum_y);
+            double t1, t2;
+            apj_warp_top2(top1, t1, t2);
+            if (lane == 0) {
+                double2 m = sm.top[wid];
+                apj_top2_merge(m.x, m.y, t1, t2);
+                sm.top[wid] = m;
+                if (SLAB && (info & (APJ_INFO_PUSH_LEFT | APJ_INFO_PUSH_RIGHT))) sm.pushed = 1;
+            }
+        }
+        if (nxt >= nblk) break;
+        tile = nxt;
+        k = k == 2 ? 0 : k + 1;
+    }
+
+    // ---- the block's partial: lanes in a shuffle tree, warps in order ----
+    {
+        double2 a = sSum[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+            a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+        }
+        if (lane == 0) sm.red[wid] = make_double4(a.x, a.y, sm.top[wid].x, sm.top[wid].y);
+        __syncthreads();
+        if (wid != 0) return;
+        double4 r = sm.red[0];
+#pragma unroll
+        for (int w = 1; w < NW; w++) {
+            const double4 b = sm.red[w];
+            r.x += b.x; r.y += b.y;
+            apj_top2_merge(r.z, r.w, b.z, b.w);
+        }
+        if (SLAB && sm.pushed) { __syncwarp(); __threadfence_system(); }
+        if (lane == 0) st.partials[blockIdx.x] = r;
+    }
 }
 
 // Split tail of the step kernel (large systems): deterministic two-level fold of the per-block partials
@@ -632,7 +890,7 @@ __global__ void __launch_bounds__(RC_TB) apj_reduce_commit_kernel(const DevState
     const int sys = blockIdx.y, c = blockIdx.x, t = threadIdx.x;
     SysCtl* __restrict__ ctl = st.ctl + sys;
     if (ctl->stale || ctl->step >= ctl->target) return;   // the step kernel exited on the same test: nothing to fold
-    const int nblk = ctl->nblk;
+    const int nblk = st.persist_grid > 0 ? min(st.persist_grid, ctl->nblk) : ctl->nblk;   // pipelined kernel: one partial per resident block
     const int nchunk = (nblk + RC_CHUNK - 1) / RC_CHUNK;
     if (c >= nchunk) return;
     const double4* __restrict__ part = st.partials + (long long)sys * st.maxblk;
@@ -720,23 +978,27 @@ __global__ void apj_slab_commit_kernel(const DevState st) {
 size_t step_smem_bytes(const DevState& st) {
     return (size_t)(st.tile_cap + 1) * 48 + (st.G > 1 ? (size_t)st.ppb * 32 : 0);
 }
+size_t pipe_smem_bytes(const DevState& st) {   // tile + per-thread running sums + per-thread first list quad
+    return (size_t)(st.tile_cap + 1) * 48 + (size_t)st.tb * 32;
+}
 
 template <int TB, int G>
 int configure(DevState& st) {
-    const int bytes = (int)step_smem_bytes(st);
-    auto set = [&](auto k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess; };
-    if (!set(apj_step_kernel<TB, G, true, false, false, false>) || !set(apj_step_kernel<TB, G, false, false, false, false>) ||
-        !set(apj_step_kernel<TB, G, true, true, false, false>) || !set(apj_step_kernel<TB, G, false, true, false, false>)) return -1;
+    const int bytes = 0;
+    auto set = [&](auto k, int) { return apj_allow_max_smem(k); };
+    if (!set(apj_step_kernel<TB, G, true, false, false>, bytes) || !set(apj_step_kernel<TB, G, false, false, false>, bytes) ||
+        !set(apj_step_kernel<TB, G, true, true, false>, bytes) || !set(apj_step_kernel<TB, G, false, true, false>, bytes)) return -1;
     st.persist_grid = 0;
     if (G == 1) {
-        if (!set(apj_step_kernel<TB, 1, true, false, true, false>) || !set(apj_step_kernel<TB, 1, false, false, true, false>) ||
-            !set(apj_step_kernel<TB, 1, true, true, true, false>) || !set(apj_step_kernel<TB, 1, false, true, true, false>)) return -1;
-        if (!set(apj_step_kernel<TB, 1, true, false, true, true>) || !set(apj_step_kernel<TB, 1, false, false, true, true>) ||
-            !set(apj_step_kernel<TB, 1, true, true, true, true>) || !set(apj_step_kernel<TB, 1, false, true, true, true>)) return -1;
-        if (st.split_tail && st.n_sys == 1 && st.want_persist) {   // one wave of resident blocks
+        if (!set(apj_step_kernel<TB, 1, true, false, true>, bytes) || !set(apj_step_kernel<TB, 1, false, false, true>, bytes) ||
+            !set(apj_step_kernel<TB, 1, true, true, true>, bytes) || !set(apj_step_kernel<TB, 1, false, true, true>, bytes)) return -1;
+        if (st.split_tail && st.n_sys == 1 && st.want_persist) {   // pipelined persistent kernel: one wave of resident blocks
+            const int pb = (int)pipe_smem_bytes(st);
+            if (!set(apj_step_pipe_kernel<TB, true, false>, pb) || !set(apj_step_pipe_kernel<TB, false, false>, pb) ||
+                !set(apj_step_pipe_kernel<TB, true, true>, pb) || !set(apj_step_pipe_kernel<TB, false, true>, pb)) return -1;
             int dev = 0, sms = 0, nb = 0;
             if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apj_step_kernel<TB, 1, false, false, true, true>, TB, bytes) != cudaSuccess) return -1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apj_step_pipe_kernel<TB, false, false>, TB, pb) != cudaSuccess || nb < 1) return -1;
             st.persist_grid = sms * nb;
             st.persist_sms = sms;
         }
@@ -744,29 +1006,43 @@ int configure(DevState& st) {
     return 0;
 }
 
-template <int TB, int G, bool SPLIT, bool PERSIST>
+template <int TB, int G, bool SPLIT>
 void launch_variant(const DevState& st, cudaStream_t s, const double* noise_by_id, int always_full) {
-    const int grid = PERSIST ? st.persist_grid : st.n_sys * st.maxblk;
+    const int grid = st.n_sys * st.maxblk;
     const size_t smem = step_smem_bytes(st);
     if (st.slab) {
-        if (noise_by_id) apj_step_kernel<TB, G, true, true, SPLIT, PERSIST><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
-        else apj_step_kernel<TB, G, false, true, SPLIT, PERSIST><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+        if (noise_by_id) apj_step_kernel<TB, G, true, true, SPLIT><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
+        else apj_step_kernel<TB, G, false, true, SPLIT><<<grid, TB, smem, s>>>(st, nullptr, always_full);
     } else {
-        if (noise_by_id) apj_step_kernel<TB, G, true, false, SPLIT, PERSIST><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
-        else apj_step_kernel<TB, G, false, false, SPLIT, PERSIST><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+        if (noise_by_id) apj_step_kernel<TB, G, true, false, SPLIT><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
+        else apj_step_kernel<TB, G, false, false, SPLIT><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+    }
+}
+template <int TB>
+void launch_pipe(const DevState& st, cudaStream_t s, const double* noise_by_id, int always_full) {
+    const int grid = st.persist_grid;
+    const size_t smem = pipe_smem_bytes(st);
+    if (st.slab) {
+        if (noise_by_id) apj_step_pipe_kernel<TB, true, true><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
+        else apj_step_pipe_kernel<TB, false, true><<<grid, TB, smem, s>>>(st, nullptr, always_full);
+    } else {
+        if (noise_by_id) apj_step_pipe_kernel<TB, true, false><<<grid, TB, smem, s>>>(st, noise_by_id, always_full);
+        else apj_step_pipe_kernel<TB, false, false><<<grid, TB, smem, s>>>(st, nullptr, always_full);
     }
 }
 
 template <int TB, int G>
 void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int always_full) {
     if (G == 1 && st.split_tail) {
-        if (st.persist_grid > 0) launch_variant<TB, 1, true, true>(st, s, noise_by_id, always_full);
-        else launch_variant<TB, 1, true, false>(st, s, noise_by_id, always_full);
+        if (st.persist_grid > 0) { launch_pipe<TB>(st, s, noise_by_id, always_full); apj_check_launch("apj_step_pipe_kernel"); }
+        else { launch_variant<TB, 1, true>(st, s, noise_by_id, always_full); apj_check_launch("apj_step_kernel (split tail)"); }
         apj_reduce_commit_kernel<<<dim3((st.maxblk + RC_CHUNK - 1) / RC_CHUNK, st.n_sys), RC_TB, 0, s>>>(st);
+        apj_check_launch("apj_reduce_commit_kernel");
     } else {
-        launch_variant<TB, G, false, false>(st, s, noise_by_id, always_full);
+        launch_variant<TB, G, false>(st, s, noise_by_id, always_full);
+        apj_check_launch("apj_step_kernel (fused tail)");
     }
-    if (st.slab) apj_slab_commit_kernel<<<1, 32, 0, s>>>(st);
+    if (st.slab) { apj_slab_commit_kernel<<<1, 32, 0, s>>>(st); apj_check_launch("apj_slab_commit_kernel"); }
 }
 
 }  // namespace
@@ -780,6 +1056,7 @@ void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int a
     else if (st.tb == 128 && st.G == 8) { CALL(128, 8); }
 
 int apj_step_blocks_per_sm_limit(int tb) { return apj_blocks_for(tb); }
+size_t apj_step_extra_smem(const DevState& st) { return (st.want_persist && st.split_tail && st.n_sys == 1 && st.G == 1) ? (size_t)st.tb * 32 : 0; }
 
 int apj_configure_kernels(DevState& st) {
 #define APJ_CFG(TB, G) return configure<TB, G>(st)

@@ -41,10 +41,10 @@ class _State(C.Structure):
 
 
 EXPORTS = ["apj_version", "apj_last_error", "apj_create", "apj_destroy", "apj_set_activity", "apj_set_ramp",
-           "apj_upload_state", "apj_download_state", "apj_state_checksum", "apj_set_com", "apj_get_com", "apj_mark_origin",
+           "apj_upload_state", "apj_download_state", "apj_state_checksum", "apj_lattice_box_length", "apj_init_lattice", "apj_get_box_table", "apj_overlap_hue", "apj_set_com", "apj_get_com", "apj_mark_origin",
            "apj_skip_self_term_once", "apj_step", "apj_step_injected", "apj_force_rebuild", "apj_sync", "apj_save_checkpoint", "apj_load_checkpoint",
            "apj_get_counters", "apj_get_sweep_stats", "apj_set_sweep_truncation", "apj_get_tuning", "apj_set_reset_counter", "apj_get_geometry", "apj_get_pair_list", "apj_get_cell_lists", "apj_list_stats",
-           "apj_order_orientation", "apj_msd", "apj_fluct_area", "apj_spatial_correlations", "apj_vel_hist",
+           "apj_order_orientation", "apj_msd", "apj_fluct_area", "apj_obs_enqueue", "apj_obs_fetch", "apj_spatial_correlations", "apj_vel_hist",
            "apj_occupancy_hist", "apj_timer_begin", "apj_timer_end", "apj_time_step_kernel",
            # slab mode (bound in slab.py)
            "apj_slab_create", "apj_slab_info", "apj_slab_export", "apj_slab_connect", "apj_slab_set_timeout", "apj_slab_ready",
@@ -72,6 +72,10 @@ def load_library():
     L.apj_upload_state.argtypes = [C.c_void_p, C.POINTER(_State)]
     L.apj_download_state.argtypes = [C.c_void_p, C.POINTER(_State)]
     L.apj_state_checksum.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.apj_lattice_box_length.argtypes = [C.c_int64, C.c_int32, C.c_uint64, _dp, C.c_int32, _dp]
+    L.apj_init_lattice.argtypes = [C.c_void_p, C.c_uint64]
+    L.apj_get_box_table.argtypes = [C.c_void_p, C.c_int32, _dp, _ip]
+    L.apj_overlap_hue.argtypes = [C.c_void_p, _ip]
     L.apj_set_com.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _dp]
     L.apj_get_com.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _dp]
     L.apj_mark_origin.argtypes = [C.c_void_p]
@@ -94,6 +98,8 @@ def load_library():
     L.apj_order_orientation.argtypes = [C.c_void_p, _dp, _dp]
     L.apj_msd.argtypes = [C.c_void_p, _dp]
     L.apj_fluct_area.argtypes = [C.c_void_p, _dp, _dp]
+    L.apj_obs_enqueue.argtypes = [C.c_void_p, C.c_int32, _dp, _lp]
+    L.apj_obs_fetch.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _dp]
     L.apj_spatial_correlations.argtypes = [C.c_void_p, C.c_double, _dp, _dp, _dp, _dp]
     L.apj_vel_hist.argtypes = [C.c_void_p, _dp, _lp]
     L.apj_occupancy_hist.argtypes = [C.c_void_p, _lp]
@@ -205,6 +211,32 @@ class DeviceEngine:
         self._chk(self.lib.apj_download_state(self.h, C.byref(st)))
         return {k: out[k] for k in fields}
 
+    @staticmethod
+    def lattice_box_length(n, dens, seed, n_systems=1, device=0):
+        """Box length of every system for the radii apj_init_lattice(seed) will draw (jamming.cpp:305)."""
+        lib = load_library()
+        d = _f64(np.broadcast_to(np.asarray(dens, dtype=np.float64), (n_systems,)).copy())
+        out = np.zeros(n_systems)
+        rc = lib.apj_lattice_box_length(int(n), int(n_systems), int(seed), _p(d), int(device), _p(out))
+        if rc != 0:
+            raise ApjError(rc, lib.apj_last_error(None).decode())
+        return out
+
+    def init_lattice(self, seed):
+        """Engine::initCells on the device (radii, jittered lattice, polarity), then binning + lists."""
+        self._chk(self.lib.apj_init_lattice(self.h, int(seed)))
+
+    def box_table(self, system=0):
+        nbox = self.geometry(system)["nbox"]
+        c, nb = np.zeros((nbox, 2)), np.zeros((nbox, 9), dtype=np.int32)
+        self._chk(self.lib.apj_get_box_table(self.h, int(system), _p(c), _p(nb, _ip)))
+        return c, nb
+
+    def overlap_hue(self):
+        o = np.zeros(self.ntot, dtype=np.int32)
+        self._chk(self.lib.apj_overlap_hue(self.h, _p(o, _ip)))
+        return o
+
     def checksum(self):
         """64-bit fingerprint of {id, x, y, cos, sin} over the particles this handle owns (apj_state_checksum)."""
         v = C.c_uint64(0)
@@ -313,6 +345,21 @@ class DeviceEngine:
         o = np.zeros(self.n_systems)
         self._chk(self.lib.apj_fluct_area(self.h, _p(r), _p(o)))
         return o
+
+    OBS_COM, OBS_ORDER, OBS_MSD, OBS_FLUCT = 0, 1, 2, 3
+
+    def obs_enqueue(self, kind, param=None):
+        """Queue a reduction on the stream (no host synchronisation); returns its ticket."""
+        p = None if param is None else _f64(np.broadcast_to(np.asarray(param, dtype=np.float64), (self.n_systems,)).copy())
+        tk = C.c_int64(0)
+        self._chk(self.lib.apj_obs_enqueue(self.h, int(kind), _p(p), C.byref(tk)))
+        return int(tk.value)
+
+    def obs_fetch(self, first, count):
+        """Raw sums of tickets first .. first+count-1: array (count, n_systems, 2), one copy + one sync."""
+        out = np.zeros((int(count), self.n_systems, 2))
+        self._chk(self.lib.apj_obs_fetch(self.h, int(first), int(count), _p(out)))
+        return out
 
     def spatial_correlations(self, cutoff):
         nc, npb = int(np.ceil(cutoff / 2.0)), int(np.ceil(cutoff / 0.1))

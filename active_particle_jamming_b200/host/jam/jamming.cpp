@@ -46,7 +46,7 @@ using namespace std::chrono;
 #include "../../../include/apj_b200.h"
 
 const bool remote = 0;      // 0: local settings (timeAvg 10, cutoff 20), 1: cluster settings (reference :28, :147-162)
-const bool makevid = 0;     // 1: Ovito frames for the last `film` steps (reference :32)
+const bool makevid = getenv("APJ_MAKEVID") && atoi(getenv("APJ_MAKEVID"));   // Ovito frames for the last `film` steps (reference :32: const 0; APJ_MAKEVID=1 films)
 
 // Initial-condition randomness (reference :36-41 uses Boost mt19937 seeded from the clock; Boost is
 // not a dependency here). Radii / lattice jitter ~ N(0,1), angles ~ U[-PI,PI) on the 2^-32 lattice.
@@ -98,6 +98,8 @@ struct Engine
     double calculateOrderParameter();
     vector<double> calculateSystemOrientation();
     void print_video(Print&);
+    void film_hue();
+    bool pulled_hue = false;
     double delta_norm(double);
     double MSD();
 
@@ -480,10 +482,27 @@ void Engine::print_video(Print& printer)
         vector<double> velocity(3, 0.0);
         velocity[0] = cell[i].vx;
         velocity[1] = cell[i].vy;
-        cell[i].over = 240;             // overlap hue is not tracked on the device
-        printer.print_Ovito(first, N, i, cell[i].R, cell[i].over, cell[i].x, velocity);
+        printer.print_Ovito(first, N, i, cell[i].R, cell[i].over, cell[i].x, velocity);   // over: film_hue() of this step
+        cell[i].over = 240;             // :866
         first = 1;
     }
+}
+
+// Cell::over of a filmed step (reference :653-656): the hue is accumulated by the neighborInteractions of THE step whose
+// frame is printed, from the positions that step starts from. All queued steps but the last are run, the device
+// evaluates the hue for that state (apj_overlap_hue: the reference's integer, update order included), then the last
+// step runs. (If that very step rebuilds the lists, the reference visits the pairs in the new lists' order; the hue
+// can then differ by one unit where two truncations fall differently.)
+void Engine::film_hue()
+{
+    if (pending < 1) return;
+    pending--;
+    flush();
+    pending = 1;
+    vector<int32_t> hue((size_t)batch->nsys*N);
+    check(apj_overlap_hue(dev, hue.data()), "apj_overlap_hue");
+    for (int i = 0; i < N; i++) cell[i].over = hue[(size_t)sys*N + i];
+    pulled_hue = true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -516,6 +535,7 @@ void Engine::tick()
     const long int corr_every = totalSteps/timeAvg;
 
     calculate_next_positions();
+    if (makevid && countdown < film && t % nSkip == 0) film_hue();   // the frame print_video writes below
 
     if (t % fluct_int == 0) { flush(); fluct->measureFluctuations(cell, COM, *printer); }
 

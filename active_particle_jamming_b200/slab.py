@@ -235,6 +235,13 @@ class _SlabFront:
     def counters(self):
         return self.local[0].counters()
 
+    def save_checkpoint(self, prefix):
+        """One file per rank, `prefix`.rank<r>of<n> (the 16M box is never gathered)."""
+        self._each(lambda r: r.save_checkpoint("%s.rank%dof%d" % (prefix, r.rank, r.nranks)))
+
+    def load_checkpoint(self, prefix):
+        self._each(lambda r: r.load_checkpoint("%s.rank%dof%d" % (prefix, r.rank, r.nranks)))
+
     def get_com(self):
         return self.local[0].get_com()
 

@@ -149,31 +149,56 @@ def run_cpu(rho, l_s, l_n, warm, steps, n=CPU_SAMPLE_N):
 CPU_MIN_STEPS = 1500      # the CPU legs time at least this many steps per Engine (rebuilds included), whatever --steps says
 
 
-def run_cadence(e, K, reps):
+def run_cadence(e, K, reps, queued=True):
     """The reference driver's measurement loop (jamming.cpp:207-255) for steps t = 0..K-1 through the C ABI:
     measureFluctuations every FLUCT_INT steps, again + order / orientation / COM / MSD every NSKIP, and TIME_AVG
     times per run assignCellsToGrid + buildVerletLists + spatialCorrelations + velDist + density_distribution,
-    followed by T_CORR steps of the orientation autocorrelation. Returns the number of observable calls."""
+    followed by T_CORR steps of the orientation autocorrelation. The reductions are QUEUED on the stream
+    (apj_obs_enqueue) and read back in one copy per NSKIP block (apj_obs_fetch); the histograms and the pair
+    correlations (10 x per run) are synchronous calls. Returns the number of observable calls."""
     calls = 0
     every = max(1, K // TIME_AVG)
     events = sorted(set(list(range(0, K, FLUCT_INT)) + list(range(0, K, NSKIP)) + list(range(every, K, every))
                         + [t + k for t in range(every, K, every) for k in range(T_CORR) if t + k < K]))
     radius = np.full(reps, 3.0)
+    queued = queued and hasattr(e, "obs_enqueue")
+    first, pending = None, 0
+    OBS_COM, OBS_ORDER, OBS_MSD, OBS_FLUCT = 0, 1, 2, 3        # include/apj_b200.h APJ_OBS_*
+
+    def q(kind, param=None):
+        nonlocal first, pending, calls
+        calls += 1
+        if not queued:
+            {OBS_FLUCT: lambda: e.fluct_area(radius), OBS_ORDER: e.order_orientation, OBS_MSD: e.msd,
+             OBS_COM: lambda: (e.get_com(0) if reps > 1 or not hasattr(e, "local") else e.get_com())}[kind]()
+            return
+        tk = e.obs_enqueue(kind, param)
+        first = tk if first is None else first
+        pending += 1
+
+    def flush():
+        nonlocal first, pending
+        if pending:
+            e.obs_fetch(first, pending)
+        first, pending = None, 0
+
     done = 0                                   # steps executed; event at t is evaluated after step t+1 (calculate_next_positions first)
     for t in events:
         if t + 1 > done:
             e.step(t + 1 - done); done = t + 1
         if t % FLUCT_INT == 0:
-            e.fluct_area(radius); calls += 1
+            q(OBS_FLUCT, radius)
         if t % NSKIP == 0:
-            e.fluct_area(radius); e.order_orientation(); e.msd(); e.get_com(0); calls += 4
+            q(OBS_FLUCT, radius); q(OBS_ORDER); q(OBS_MSD); q(OBS_COM)
+            flush()
         if t % every == 0 and t != 0:
-            e.force_rebuild(); e.order_orientation(); e.spatial_correlations(CUTOFF); e.vel_hist(np.full(reps, 0.001)); e.occupancy_hist()
-            calls += 4
+            e.force_rebuild(); q(OBS_ORDER); e.spatial_correlations(CUTOFF); e.vel_hist(np.full(reps, 0.001)); e.occupancy_hist()
+            calls += 3
         if t >= every and (t % every) < T_CORR:
-            e.order_orientation(); calls += 1
+            q(OBS_ORDER)
     if done < K:
         e.step(K - done)
+    flush()
     return calls
 
 

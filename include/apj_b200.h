@@ -92,6 +92,22 @@ int apj_set_ramp(apj_engine* e, int64_t tthermalize);
  * buildVerletLists, start() :184-185) WITHOUT touching x_old. */
 int apj_upload_state(apj_engine* e, const apj_state* host);
 int apj_download_state(apj_engine* e, apj_state* host);
+/* Engine::initCells on the device (jamming.cpp:285-354, 2D branch), for systems too large to build vector<Cell> on the
+ * host: radii 1 + N(0,1)/10, jittered offset-row lattice (spacing L / floor(sqrt N), even rows shifted by 1), polarity
+ * U[-PI, PI), x_real = x0 = x_old = x, v = 0, COM; then assignCellsToGrid + buildVerletLists. The variates come from
+ * the Philox stream keyed by `seed` (Box-Muller normals); the reference's own stream is time-seeded, so parity of the
+ * initial condition is distributional. Two calls, because the box length depends on the radii:
+ *   apj_lattice_box_length  L[s] = sqrt(PI * sum R^2 / dens[s])  (:305)  for the radii `seed` will produce
+ *   apj_create(.., L, ..), then apj_init_lattice(e, seed)         (the same seed)                                 */
+int apj_lattice_box_length(int64_t n, int32_t n_systems, uint64_t seed, const double* dens, int32_t device, double* L_out);
+int apj_init_lattice(apj_engine* e, uint64_t seed);
+/* Engine::topology (jamming.cpp:356-410) as a table, computed on the device: centres[2*nbox] = Box::center, neighbors[9*nbox] =
+ * Box::neighbors, reference numbering p = i + j*b. (The kernels never read such a table: they derive both on the fly.) */
+int apj_get_box_table(apj_engine* e, int32_t system, double* centres, int32_t* neighbors);
+/* Cell::over as neighborInteractions leaves it on a filmed step (jamming.cpp:653-656) for the CURRENT state and lists:
+ * 240 minus 240 |overlap| per overlapping pair, accumulated into an int in the reference's update order (every update
+ * truncates). over[n_systems * n] by particle id; call it before the step whose frame print_video writes (:855-870). */
+int apj_overlap_hue(apj_engine* e, int32_t* over);
 /* Both copy the caller's arrays field by field (cudaMemcpyAsync on the handle's stream: page-locked caller
  * buffers move at PCIe speed, pageable ones work but are staged by the driver) through staging planes in
  * HBM; the AoS <-> SoA interleave, Rinv, cos/sin(phi), box renumbering and the by-id scatter run in kernels.
@@ -128,7 +144,9 @@ int apj_sync(apj_engine* e);
  * in original particle order. apj_load_checkpoint needs a handle of the same shape (n, n_systems, L, dt, rn,
  * rs); it restores the Philox key and step, re-bins and rebuilds the lists from the stored positions and keeps
  * x_old / COM_old, so the continuation follows the uninterrupted run to rounding (not bit for bit: the fresh
- * lists are ordered differently). Periodic handles only. */
+ * lists are ordered differently). On a slab handle both calls are [collective] and work on THIS rank's share:
+ * every rank writes / reads its own file (owned particles with their ids; no gather of the box), and a file
+ * can only be loaded by the rank of the decomposition that wrote it. */
 int apj_save_checkpoint(apj_engine* e, const char* path);
 int apj_load_checkpoint(apj_engine* e, const char* path);
 
@@ -172,6 +190,21 @@ int apj_msd(apj_engine* e, double* msd);
 /* Inner loop of Fluctuations::measureFluctuations (classes/Fluctuations.h:62-76): total lens
  * area between every disk and a circle of radius[s] centred on COM. */
 int apj_fluct_area(apj_engine* e, const double* radius, double* area);
+/* Queued form of the four reductions above: the measurement is placed on the handle's stream behind the steps
+ * already issued and returns at once; its raw sums (two doubles per system) are kept in a device-side ring of the
+ * last 4096 tickets and apj_obs_fetch reads any run of them back with ONE copy and ONE synchronisation. The
+ * reference's cadence (measureFluctuations every 10 steps, order / MSD every 100; jamming.cpp:211-239) then runs
+ * without a host round trip per measurement. Raw sums per kind:
+ *   APJ_OBS_COM    {sum x_real, sum y_real}                 (divide by N: calculate_COM, :761-774)
+ *   APJ_OBS_ORDER  {sum vx/|v|, sum vy/|v|}                  (order = |.|/N :788, orientation = ./N :803)
+ *   APJ_OBS_MSD    {sum of squared COM-corrected displacements, 0}   (divide by N, :822)
+ *   APJ_OBS_FLUCT  {lens-area sum for radius param[s], 0}    (Fluctuations.h:62-76)                              */
+#define APJ_OBS_COM 0
+#define APJ_OBS_ORDER 1
+#define APJ_OBS_MSD 2
+#define APJ_OBS_FLUCT 3
+int apj_obs_enqueue(apj_engine* e, int32_t kind, const double* param, int64_t* ticket);
+int apj_obs_fetch(apj_engine* e, int64_t first_ticket, int64_t count, double* out /* count x n_systems x 2 */);
 /* Correlations::spatialCorrelations raw sums (classes/Correlations.h:71-152) for one call:
  * counts[nc], ori_sum[nc], vel_sum[nc], pair_sum[np] per system (rows of nc / np), with
  * nc = ceil(cutoff/2.0), np = ceil(cutoff/0.1). Normalisation (:154-166) is left to the host. */

@@ -292,6 +292,28 @@ void orc_neighbor_interactions(orc_sim* s, const double* noise) {
     }
 }
 /* Cell::update, 2D branch, classes/Cell.h:92-118 + PBC :157 (SURVEY Q6 order). */
+/* Cell::over on a filmed step (jamming.cpp:653-656): int over -= 240*abs(overlap) for both partners of every
+ * overlapping pair, in the order neighborInteractions visits the half lists; `over` is an int, so every update
+ * truncates toward zero. Starts from 240 (print_video, :866). */
+void orc_overlap_hue(const orc_sim* s, int* over) {
+    for (long i = 0; i < s->N; i++) over[i] = 240;
+    for (long i = 0; i < s->N; i++)
+        for (long k = s->vl_off[i]; k < s->vl_off[i + 1]; k++) {
+            long j = s->vl_idx[k];
+            double dx = delta_norm(s, s->x[j] - s->x[i]);
+            double dy = delta_norm(s, s->y[j] - s->y[i]);
+            double d2 = dx * dx + dy * dy;
+            if (d2 < s->rn2) {
+                double sumR = s->R[i] + s->R[j];
+                if (d2 < sumR * sumR) {
+                    double overlap = sumR / sqrt(d2) - 1;
+                    over[i] = (int)(over[i] - 240 * fabs(overlap));
+                    over[j] = (int)(over[j] - 240 * fabs(overlap));
+                }
+            }
+        }
+}
+
 void orc_update(orc_sim* s) {
     for (long i = 0; i < s->N; i++) {
         s->phi[i] = wrap_angle(s->phi[i]);

@@ -88,6 +88,7 @@ class OracleSim:
             L.orc_get_cell_lists.restype = C.c_long
             L.orc_get_cell_lists.argtypes = [C.c_void_p, _lp, _ip]
             L.orc_get_box_neighbors.argtypes = [C.c_void_p, _ip]
+            L.orc_overlap_hue.argtypes = [C.c_void_p, _ip]
             L.orc_new_skin_list.restype = C.c_int
             L.orc_new_skin_list.argtypes = [C.c_void_p]
             L.orc_neighbor_interactions.argtypes = [C.c_void_p, _dp]
@@ -197,6 +198,12 @@ class OracleSim:
         nbox = int(self.scalars()["nbox"])
         o = np.zeros((nbox, 9), dtype=np.int32)
         self.l.orc_get_box_neighbors(self.h, _ptr(o, _ip))
+        return o
+
+    def overlap_hue(self):
+        """Cell::over after neighborInteractions of a filmed step (jamming.cpp:653-656), by particle index."""
+        o = np.zeros(self.N, dtype=np.int32)
+        self.l.orc_overlap_hue(self.h, _ptr(o, _ip))
         return o
 
     def save_old(self):
@@ -357,6 +364,7 @@ class RefEngine:
             L.apjref_corr_dims.argtypes = [C.c_void_p, _ip]
             L.apjref_spatial_correlations.argtypes = [C.c_void_p, _dp, _dp, _dp]
             L.apjref_vel_dist.argtypes = [C.c_void_p, _dp]
+            L.apjref_overlap_hue.argtypes = [C.c_void_p, _ip]
             L.apjref_autocorrelation.argtypes = [C.c_void_p, C.c_int, _dp]
             L.apjref_run_start.restype = C.c_double
             L.apjref_run_start.argtypes = [C.c_void_p, C.c_char_p]
@@ -441,6 +449,13 @@ class RefEngine:
 
     def new_skin_list(self):
         return bool(self.l.apjref_new_skin_list(self.h))
+
+    def overlap_hue(self):
+        """Cell::over left by the reference's own neighborInteractions on a filmed step (scratch engines only:
+        forces and alignment sums accumulate as in any call)."""
+        o = np.zeros(self.N, dtype=np.int32)
+        self.l.apjref_overlap_hue(self.h, _ptr(o, _ip))
+        return o
 
     def save_old(self):
         self.l.apjref_save_old(self.h)

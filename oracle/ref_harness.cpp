@@ -162,6 +162,18 @@ void apjref_neighbor_interactions(void* h) { E(h).neighborInteractions(); }
 void apjref_calculate_com(void* h) { E(h).calculate_COM(); }
 void apjref_save_old(void* h) { E(h).saveOldPositions(); }
 void apjref_step(void* h) { E(h).calculate_next_positions(); }
+// Cell::over (the Ovito hue, jamming.cpp:653-656): run neighborInteractions with the filming condition
+// (countdown <= film && t % nSkip == 0) switched on, read the hue, restore the clock. Forces and alignment sums
+// accumulate as in any call of neighborInteractions: the caller works on a scratch engine.
+void apjref_overlap_hue(void* h, int* over) {
+    Engine& e = E(h);
+    const long t0 = e.t, c0 = e.countdown;
+    for (long i = 0; i < e.N; i++) e.cell[i].over = 240;          // print_video leaves 240 behind (:866)
+    e.t = 0; e.countdown = 1;
+    e.neighborInteractions();
+    e.t = t0; e.countdown = c0;
+    for (long i = 0; i < e.N; i++) over[i] = e.cell[i].over;
+}
 void apjref_steps(void* h, long n) { for (long k = 0; k < n; k++) E(h).calculate_next_positions(); }
 void apjref_relax(void* h) { E(h).relax(); }
 double apjref_delta_norm(void* h, double d) { return E(h).delta_norm(d); }

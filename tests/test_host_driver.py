@@ -114,6 +114,30 @@ def test_full_run_matches_reference_output_tree(jam, tmp_path):
 
 
 @pytest.mark.gpu
+def test_video_frames_carry_the_overlap_hue(jam, tmp_path):
+    """print_video (jamming.cpp:855-870; makevid is a compile-time 0 in the reference, APJ_MAKEVID=1 films here): one XYZ
+    frame per nSkip steps in the reference's layout (classes/Print.h:129-148), third column = Cell::over, the integer hue
+    apj_overlap_hue evaluates for the step of the frame (240 = no overlap, lower = compressed)."""
+    N, steps = 400, 300
+    env = dict(os.environ, APJ_OUTPUT_ROOT=str(tmp_path), APJ_SEED="7", APJ_MAKEVID="1")
+    r = subprocess.run([jam, "vid", "run0", str(N), str(steps), "0.1", "0.3", "1.0"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = open(os.path.join(str(tmp_path), "local_output", "vid", "run0", "vid", "ovito.txt")).read().split("\n")[:-1]
+    frames = steps // 100 + 1                                    # t = 0, 100, 200, 300
+    assert len(lines) == frames * (N + 2)
+    hues = []
+    for f in range(frames):
+        blk = lines[f * (N + 2):(f + 1) * (N + 2)]
+        assert blk[0] == str(N) and blk[1] == "time step comment"
+        rows = [l.split("\t") for l in blk[2:]]
+        assert all(len(c) == 7 for c in rows) and [int(c[0]) for c in rows] == list(range(N))
+        hues.append(np.array([int(c[2]) for c in rows]))
+    h = np.concatenate(hues)
+    assert h.max() == 240 and h.min() < 236 and np.all(h <= 240)  # rho = 1.0: above jamming, many overlapping pairs
+    assert np.mean(h < 240) > 0.3
+
+
+@pytest.mark.gpu
 def test_engine_mirrors_expose_reference_state(tmp_path):
     """Cell / Box mirrors: pull_cells, pull_cell_lists, pull_verlet_lists give the reference's views."""
     prog = r'''

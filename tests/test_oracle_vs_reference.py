@@ -75,3 +75,26 @@ def test_uniform_mapping_matches_shimmed_randuni():
     want = [OracleSim.lib().orc_u32_to_randuni(int(u)) for u in raw]
     assert got == want
     assert all(-PI <= g < PI for g in got)
+
+
+@pytest.mark.parametrize("N,rho,seed", [(400, 1.0, 3), (1500, 0.9, 4)])
+def test_overlap_hue_matches_reference_neighbor_interactions(N, rho, seed):
+    """Cell::over (the Ovito hue; jamming.cpp:653-656): the oracle's restatement equals what the reference's own
+    neighborInteractions leaves behind on a filmed step -- an int accumulated with truncation at every update,
+    so the ORDER of the pair visits matters."""
+    RefEngine.seed(seed)
+    r = RefEngine(N, 1000, 0.3, 0.3, rho)
+    r.init_cells(); r.topology(); r.assign(); r.build(); r.mark_origin()
+    rng = np.random.default_rng(seed)
+    for _ in range(15):
+        r.step(rng.uniform(-PI, PI, N))
+    r.assign(); r.build()
+    s = r.get_state()
+    o = oracle_from_state(s, rho)
+    o.assign(bruteforce=True); o.build()
+    want = r.overlap_hue()
+    got = o.overlap_hue()
+    assert np.array_equal(got, want)
+    assert want.min() < 236 and want.max() == 240          # some particles overlap visibly, some not at all
+    r.close()
+    o.close()
