@@ -393,6 +393,7 @@ void apj_launch_init_lattice(const DevState& st, cudaStream_t s, unsigned long l
 void apj_launch_box_table(const DevState& st, cudaStream_t s, int sys, double* d_centres, int* d_neighbors);
 void apj_launch_overlap_hue(const DevState& st, cudaStream_t s, int* d_over_by_id);
 void apj_launch_step(const DevState& st, const ApjLaunch& l, const double* noise_by_id, int always_full);
+void apj_launch_step_parts(const DevState& st, const ApjLaunch& l, void (*between)(int, void*), void* arg);
 void apj_launch_rebuild_chain(const DevState& st, const ApjLaunch& l, int max_nbox, int max_b);
 int apj_rebuild_chain_launches(const DevState& st);
 int apj_configure_kernels(DevState& st);   // also sets st.persist_grid

@@ -1246,6 +1246,44 @@ extern "C" int apj_time_step_kernel(apj_engine* e, int64_t n, float* mean_ms, in
     return check_overflow(e);
 }
 
+// Per-part timing of a step: event after the step kernel, after the fold + commit kernel and after the slab commit
+// (the all-rank rendezvous), n single steps; out3 = mean ms of the three parts (zeros where a part does not exist).
+extern "C" int apj_time_step_parts(apj_engine* e, int64_t n, float* out3) {
+    if (!e || n < 1 || n > 1024 || !out3) return APJ_E_INVALID;
+    if (!e->have_state) return fail(e, APJ_E_STATE, "apj_time_step_parts: no state uploaded");
+    DevState& st = e->st;
+    struct Events {
+        std::vector<cudaEvent_t> v;
+        cudaStream_t s; int k;
+        ~Events() { for (auto x : v) if (x) cudaEventDestroy(x); }
+    } evs;
+    evs.v.assign(4 * n, nullptr);
+    evs.s = e->stream; evs.k = 0;
+    for (auto& x : evs.v) APJ_CUDA(e, cudaEventCreate(&x));
+    ApjLaunch l = launcher(e, true);
+    apj_add_target_kernel<<<(st.n_sys + 63) / 64, 64, 0, e->stream>>>(st.ctl, st.n_sys, n);
+    e->launches++;
+    for (int64_t k = 0; k < n; k++) {
+        evs.k = (int)(4 * k);
+        APJ_CUDA(e, cudaEventRecord(evs.v[4 * k], e->stream));
+        apj_launch_step_parts(st, l, [](int part, void* a) { Events* ev = static_cast<Events*>(a); cudaEventRecord(ev->v[ev->k + 1 + part], ev->s); }, &evs);
+        apj_launch_rebuild_chain(st, l, e->max_nbox, e->max_b);
+    }
+    APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    double tot[3] = {0, 0, 0};
+    for (int64_t k = 0; k < n; k++)
+        for (int p = 0; p < 3; p++) { float ms = 0; APJ_CUDA(e, cudaEventElapsedTime(&ms, evs.v[4 * k + p], evs.v[4 * k + p + 1])); tot[p] += ms; }
+    for (int p = 0; p < 3; p++) out3[p] = (float)(tot[p] / n);
+    if (int rc = pull_ctl(e)) return rc;
+    long long remaining;
+    for (int a = 0; a < 256 && !all_done(e, &remaining); a++) {   // launches dropped by a rebuild: finish the series
+        apj_launch_step(st, l, nullptr, 0);
+        apj_launch_rebuild_chain(st, l, e->max_nbox, e->max_b);
+        if (int rc = pull_ctl(e)) return rc;
+    }
+    return check_overflow(e);
+}
+
 // ---- slab mode: one global periodic box over the GPUs of a node (BASELINE config 4) ----
 extern "C" int apj_slab_create(const apj_config* cfg, double L, int32_t rank, int32_t nranks, int64_t capacity, apj_engine** out) {
     SlabSpec sp;

@@ -27,6 +27,7 @@
 // decision therefore falls on exactly the step the reference takes it on, with no host round
 // trip and no extra pass over the particles.
 #include "apj_device.cuh"
+#include "apj_trig.h"
 
 namespace {
 
@@ -173,7 +174,7 @@ __device__ __forceinline__ void apj_new_orientation(const double ax, const doubl
         // ay = -0.0 with ax < 0 is theta = -pi): for eta > 0 (theta >= 0 required) phi >= PI iff
         // sin(phi) < 0, or cos(phi) < 0 and sin(phi) <= sin(PI); mirrored for eta < 0.
         double sn_n, cn_n;
-        sincos(nz, &sn_n, &cn_n);
+        apj_sincos_pm3(nz, &sn_n, &cn_n);                 // |nz| <= 3 here (apj_trig.h): half the instructions of sincos()
         const double inv = rsqrt(r2);
         const double c0 = ax * inv, s0 = ay * inv;
         cs = c0 * cn_n - s0 * sn_n;
@@ -852,6 +853,30 @@ apj_step_pipe_kernel(const DevState st, const double* __restrict__ noise_by_id, 
     }
 }
 
+// one warp: wait for the partials of all ranks, fold them in rank order, take the decision
+__device__ __forceinline__ void apj_slab_commit_warp(const DevState& st, SysCtl* __restrict__ ctl) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long ep = ctl->seq[0];
+    bool ok = true;
+    if (lane < st.nranks && !ctl->slab_err) ok = apj_wait_flag(&st.mail->flag[0][lane], ep + 1, st.timeout_ns);
+    const unsigned missing = __ballot_sync(0xffffffffu, !ok);
+    if (lane != 0) return;
+    ctl->seq[0] = ep + 1;
+    if (missing || ctl->slab_err) {   // a peer never showed up: stop stepping, the host reports it
+        if (missing && !ctl->slab_diag) ctl->slab_diag = (1 << 16) | (int)missing;
+        ctl->slab_err |= 1;
+        ctl->target = ctl->step;
+        return;
+    }
+    double4 a = make_double4(0.0, 0.0, 0.0, 0.0);
+    for (int r = 0; r < st.nranks; r++) {
+        const double2* q = reinterpret_cast<const double2*>(&st.mail->part[ep & 1][r]);
+        const double2 b01 = __ldcg(q), b23 = __ldcg(q + 1);
+        a.x += b01.x; a.y += b01.y;
+        apj_top2_merge(a.z, a.w, b23.x, b23.y);
+    }
+    apj_commit(ctl, st, a, apj_sweep_class(ctl, st));   // N of the global box; every rank folds the same partials
+}
 // Split tail of the step kernel (large systems): deterministic two-level fold of the per-block partials
 // {sum x_real, sum y_real, top-1, top-2 d2}, then the commit (periodic box) or the push of this rank's
 // partial to every rank (slab mode; apj_slab_commit_kernel follows). grid = (chunks, n_sys), RC_TB threads;
@@ -938,6 +963,8 @@ __global__ void __launch_bounds__(RC_TB) apj_reduce_commit_kernel(const DevState
             __threadfence_system();
             apj_st_release_sys(&m->flag[0][st.rank], ep + 1);
         }
+        __syncwarp();
+        apj_slab_commit_warp(st, ctl);   // second half of the step in the same launch: all-rank fold + decision
         return;
     }
     if (lane == 0) {
@@ -952,27 +979,7 @@ __global__ void __launch_bounds__(RC_TB) apj_reduce_commit_kernel(const DevState
 __global__ void apj_slab_commit_kernel(const DevState st) {
     SysCtl* __restrict__ ctl = st.ctl;
     if (ctl->stale || ctl->step >= ctl->target) return;   // the step kernel exited on the same test: nothing was sent
-    const int lane = threadIdx.x;
-    const unsigned long long ep = ctl->seq[0];
-    bool ok = true;
-    if (lane < st.nranks && !ctl->slab_err) ok = apj_wait_flag(&st.mail->flag[0][lane], ep + 1, st.timeout_ns);
-    const unsigned missing = __ballot_sync(0xffffffffu, !ok);
-    if (lane != 0) return;
-    ctl->seq[0] = ep + 1;
-    if (missing || ctl->slab_err) {   // a peer never showed up: stop stepping, the host reports it
-        if (missing && !ctl->slab_diag) ctl->slab_diag = (1 << 16) | (int)missing;
-        ctl->slab_err |= 1;
-        ctl->target = ctl->step;
-        return;
-    }
-    double4 a = make_double4(0.0, 0.0, 0.0, 0.0);
-    for (int r = 0; r < st.nranks; r++) {
-        const double2* q = reinterpret_cast<const double2*>(&st.mail->part[ep & 1][r]);
-        const double2 b01 = __ldcg(q), b23 = __ldcg(q + 1);
-        a.x += b01.x; a.y += b01.y;
-        apj_top2_merge(a.z, a.w, b23.x, b23.y);
-    }
-    apj_commit(ctl, st, a, apj_sweep_class(ctl, st));   // N of the global box; every rank folds the same partials
+    apj_slab_commit_warp(st, ctl);
 }
 
 size_t step_smem_bytes(const DevState& st) {
@@ -1042,7 +1049,7 @@ void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int a
         launch_variant<TB, G, false>(st, s, noise_by_id, always_full);
         apj_check_launch("apj_step_kernel (fused tail)");
     }
-    if (st.slab) { apj_slab_commit_kernel<<<1, 32, 0, s>>>(st); apj_check_launch("apj_slab_commit_kernel"); }
+    if (st.slab && !(G == 1 && st.split_tail)) { apj_slab_commit_kernel<<<1, 32, 0, s>>>(st); apj_check_launch("apj_slab_commit_kernel"); }
 }
 
 }  // namespace
@@ -1065,9 +1072,34 @@ int apj_configure_kernels(DevState& st) {
     return -1;
 }
 
+// The kernels of ONE step launched one by one with `between(k)` called after part k (0: step kernel, 1: fold + commit,
+// 2: slab commit) -- apj_time_step_parts records events there. Same kernels, same order as apj_launch_step.
+template <int TB, int G>
+static void launch_parts(const DevState& st, cudaStream_t s, void (*between)(int, void*), void* arg) {
+    if (G == 1 && st.split_tail) {
+        if (st.persist_grid > 0) launch_pipe<TB>(st, s, nullptr, 0);
+        else launch_variant<TB, 1, true>(st, s, nullptr, 0);
+        between(0, arg);
+        apj_reduce_commit_kernel<<<dim3((st.maxblk + RC_CHUNK - 1) / RC_CHUNK, st.n_sys), RC_TB, 0, s>>>(st);
+        between(1, arg);
+    } else {
+        launch_variant<TB, G, false>(st, s, nullptr, 0);
+        between(0, arg);
+        between(1, arg);
+    }
+    if (st.slab && !(G == 1 && st.split_tail)) apj_slab_commit_kernel<<<1, 32, 0, s>>>(st);
+    between(2, arg);
+}
+void apj_launch_step_parts(const DevState& st, const ApjLaunch& l, void (*between)(int, void*), void* arg) {
+#define APJ_PARTS(TB, G) launch_parts<TB, G>(st, l.stream, between, arg)
+    APJ_DISPATCH(APJ_PARTS)
+#undef APJ_PARTS
+    if (l.launch_counter) (*l.launch_counter) += (st.G == 1 && st.split_tail) ? 2 : (st.slab ? 2 : 1);
+}
+
 void apj_launch_step(const DevState& st, const ApjLaunch& l, const double* noise_by_id, int always_full) {
 #define APJ_LAUNCH(TB, G) launch<TB, G>(st, l.stream, noise_by_id, always_full)
     APJ_DISPATCH(APJ_LAUNCH)
 #undef APJ_LAUNCH
-    if (l.launch_counter) (*l.launch_counter) += 1 + (st.slab ? 1 : 0) + ((st.G == 1 && st.split_tail) ? 1 : 0);
+    if (l.launch_counter) (*l.launch_counter) += (st.G == 1 && st.split_tail) ? 2 : (st.slab ? 2 : 1);
 }

@@ -45,7 +45,7 @@ EXPORTS = ["apj_version", "apj_last_error", "apj_create", "apj_destroy", "apj_se
            "apj_skip_self_term_once", "apj_step", "apj_step_injected", "apj_force_rebuild", "apj_sync", "apj_save_checkpoint", "apj_load_checkpoint",
            "apj_get_counters", "apj_get_sweep_stats", "apj_set_sweep_truncation", "apj_get_tuning", "apj_set_reset_counter", "apj_get_geometry", "apj_get_pair_list", "apj_get_cell_lists", "apj_list_stats",
            "apj_order_orientation", "apj_msd", "apj_fluct_area", "apj_obs_enqueue", "apj_obs_fetch", "apj_spatial_correlations", "apj_vel_hist",
-           "apj_occupancy_hist", "apj_timer_begin", "apj_timer_end", "apj_time_step_kernel",
+           "apj_occupancy_hist", "apj_timer_begin", "apj_timer_end", "apj_time_step_kernel", "apj_time_step_parts",
            # slab mode (bound in slab.py)
            "apj_slab_create", "apj_slab_info", "apj_slab_export", "apj_slab_connect", "apj_slab_set_timeout", "apj_slab_ready",
            "apj_slab_upload", "apj_slab_download", "apj_slab_get_pairs"]
@@ -106,6 +106,7 @@ def load_library():
     L.apj_timer_begin.argtypes = [C.c_void_p]
     L.apj_timer_end.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.apj_time_step_kernel.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_float), _lp]
+    L.apj_time_step_parts.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -387,6 +388,12 @@ class DeviceEngine:
         ms = C.c_float(0)
         self._chk(self.lib.apj_timer_end(self.h, C.byref(ms)))
         return ms.value
+
+    def time_step_parts(self, n):
+        """Mean ms of {step kernel, fold + commit kernel, slab commit} over n single steps."""
+        o = (C.c_float * 3)()
+        self._chk(self.lib.apj_time_step_parts(self.h, int(n), o))
+        return [float(v) for v in o]
 
     def time_step_kernel(self, n):
         ms = C.c_float(0)

@@ -233,13 +233,13 @@ def main():
         if rank != 0:
             return
         steps_cpu = max(K, CPU_MIN_STEPS)
-        c = run_cpu(rho, l_s, l_n, max(W, 200), steps_cpu)
+        c = run_cpu(rho, l_s, l_n, max(W, 200), steps_cpu, n=min(CPU_SAMPLE_N, n_tot))
         line = {"impl": "reference", "metric": "particle-steps/sec (fp64)", "value": c["value"], "unit": "particle-steps/s",
                 "n_gpus": a.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * c["secs"] / steps_cpu, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": a.workload, "what": what, "phi": rho, "lambda_s": l_s, "lambda_n": l_n,
                            "particles": c["particles_timed"], "particles_timed": c["particles_timed"], "engines": c["engines"],
-                           "particles_per_engine": CPU_SAMPLE_N, "steps_timed": c["steps_timed"], "workload_particles": n_tot,
+                           "particles_per_engine": min(CPU_SAMPLE_N, n_tot), "steps_timed": c["steps_timed"], "workload_particles": n_tot,
                            "note": "BOUNDED SAMPLE, not the workload's configuration: the reference is a serial program whose parallel model is a job "
                                    "array, so the arm runs one Engine of N=%d per host core for max(--steps, %d) steps (rebuilds inside) and reports the "
                                    "summed particle-steps/s. Its cost per particle-step grows with N (cache misses, O(N nbox) binning), so this rate is "
@@ -351,12 +351,16 @@ def main():
     n_full, list_max = e.list_stats() if slab else e.list_stats(0)
     barrier()
     kms, committed = me.time_step_kernel(min(max(K, 16), 512))
+    barrier()
+    parts = me.time_step_parts(min(max(K, 16), 128))                       # {step kernel, fold + commit, slab commit (rendezvous)}
     per_rank = None
     if world > 1:                                                          # per-rank kernel time and share (load balance of the slabs)
-        t = torch.tensor([kms, float(n_loc)], dtype=torch.float64, device="cuda")
+        t = torch.tensor([kms, float(n_loc)] + parts, dtype=torch.float64, device="cuda")
         allt = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
-        per_rank = {"kernel_ms": [float(v[0]) for v in allt], "particles": [int(v[1]) for v in allt]}
+        per_rank = {"kernel_ms": [float(v[0]) for v in allt], "particles": [int(v[1]) for v in allt],
+                    "step_kernel_ms": [float(v[2]) for v in allt], "fold_commit_ms": [float(v[3]) for v in allt],
+                    "slab_commit_ms": [float(v[4]) for v in allt]}
         kms = max(per_rank["kernel_ms"])
     b_alg = 128.0 + 4.0 * n_full                                           # bytes per particle-step
     peaks = {}
@@ -368,7 +372,9 @@ def main():
     achieved = n_loc * reps * b_alg / (kms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "frac_of_nominal_8000": achieved / 8000.0,
-                "kernel": "apj_step_kernel (+ apj_reduce_commit_kernel)", "kernel_ms": kms, "bytes_per_particle_step": b_alg, "n_full": n_full,
+                "kernel": "apj_step_kernel (+ apj_reduce_commit_kernel)", "kernel_ms": kms,
+                "parts_ms": {"step_kernel": parts[0], "fold_commit": parts[1], "slab_commit": parts[2],
+                             "how": "events between the kernels of single steps (apj_time_step_parts)"}, "bytes_per_particle_step": b_alg, "n_full": n_full,
                 "algorithmic": "achieved = particles x (128 + 4 n_full) B / kernel time: SURVEY 8(d)'s per-particle-step figure with the FULL list "
                                "length, whatever the kernel really moves (16-bit list entries, skin-truncated sweeps); `traffic` is the measured DRAM figure",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
@@ -454,7 +460,7 @@ def main():
     if e2e:
         line["e2e"] = e2e
     if rank == 0 and world == 1 and not a.no_cpu:
-        c = run_cpu(rho, l_s, l_n, 200, CPU_MIN_STEPS)
+        c = run_cpu(rho, l_s, l_n, 200, CPU_MIN_STEPS, n=min(CPU_SAMPLE_N, n_tot))
         line["cpu_baseline"] = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample", "per_core")}
     e.close()
     if rank == 0:

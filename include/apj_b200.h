@@ -220,6 +220,9 @@ int apj_timer_end(apj_engine* e, float* milliseconds);
 /* Per-kernel timing of the fused step kernel: launches n single steps with an event pair around
  * each launch of the step (step kernel + its fold/commit kernel) and returns the mean duration (ms). */
 int apj_time_step_kernel(apj_engine* e, int64_t n, float* mean_ms, int64_t* committed);
+/* The same, split: out3 = mean duration (ms) of {step kernel, fold + commit kernel, slab commit = all-rank rendezvous}
+ * over n single steps ([collective] on slab handles). */
+int apj_time_step_parts(apj_engine* e, int64_t n, float* out3);
 
 /* ---- slab mode: ONE periodic box over the GPUs of a node (BASELINE config 4) --------
  * The global b x b cell grid (Engine::topology, jamming.cpp:356-480) is cut along x into slabs of

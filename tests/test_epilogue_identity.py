@@ -73,3 +73,19 @@ def test_identity_on_the_axes_and_near_the_wrap():
         cr, sr, wr = reference_form(a, b, eta)
         assert np.array_equal(wf, wr), (ax, ay)
         assert np.max(np.abs(cf - cr)) <= 2e-15 and np.max(np.abs(sf - sr)) <= 2e-15, (ax, ay)
+
+
+def test_noise_sincos_kernel_is_good_to_an_ulp(tmp_path):
+    """csrc/apj_trig.h (Cody-Waite reduction + minimax kernels, explicit fma) replaces the library sincos() for the
+    noise term, |x| <= 3: compiled for the host and compared with long double on 4e6 arguments incl. the reduction
+    ties near odd multiples of pi/4 and tiny arguments. Error <= 1 ulp of the result, <= 2.3e-16 absolute."""
+    import re
+    import subprocess
+    exe = str(tmp_path / "trig_probe")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "active_particle_jamming_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "trig_probe.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    m = re.search(r"worst sin err ([0-9.]+) half-ulps.*worst cos err ([0-9.]+) half-ulps.*abs>2.3e-16: (\d+)", out)
+    assert m, out
+    assert float(m.group(1)) <= 2.0 and float(m.group(2)) <= 2.0 and int(m.group(3)) == 0, out
+    assert "apj_sincos_pm3(nz, &sn_n, &cn_n)" in SRC                # ... and it is what the kernel calls
