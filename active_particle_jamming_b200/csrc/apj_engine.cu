@@ -1173,11 +1173,36 @@ extern "C" int apj_obs_fetch(apj_engine* e, int64_t first_ticket, int64_t count,
 extern "C" int apj_spatial_correlations(apj_engine* e, double cutoff, double* counts, double* ori, double* vel, double* pair) {
     APJ_NEED_STATE("apj_spatial_correlations");
     if (!(cutoff > 0) || !counts || !ori || !vel || !pair) return APJ_E_INVALID;
-    if (e->st.slab) return fail(e, APJ_E_STATE, "apj_spatial_correlations: not available on a slab handle (needs a halo of the cutoff width)");
+    if (e->st.slab && e->st.nranks > 1) return fail(e, APJ_E_STATE, "apj_spatial_correlations: slab handle, use apj_slab_spatial_correlations (pairs across the slab edges need the neighbour's edge particles)");
     // nc*dr_c must not exceed the cutoff, or the reference's boxPairs filter (jamming.cpp:460-479)
     // would decide membership of the last bin; its own settings (20, 140) are multiples of 2.
     if (std::fmod(cutoff, 2.0) != 0.0) return fail(e, APJ_E_INVALID, "apj_spatial_correlations: cutoff must be a multiple of dr_c = 2");
     APJ_OBS(apj_obs_spatial(&e->obs, e->st, e->stream, &e->launches, e->hctl.data(), cutoff, counts, ori, vel, pair, e->allocs));
+}
+// ---- Correlations::spatialCorrelations on a decomposed box (halo of the cutoff width) ----
+extern "C" int apj_slab_export_edge(apj_engine* e, double width, int64_t cap, double* out6, int64_t* n) {
+    APJ_NEED_STATE("apj_slab_export_edge");
+    if (!e->st.slab || !(width > 0) || !n || cap < 0) return APJ_E_INVALID;
+    long long found = 0;
+    if (int rc = apj_obs_export_edge(e->st, e->stream, &e->launches, width, cap, out6, &found)) return fail(e, rc, cudaGetErrorString(cudaGetLastError()));
+    *n = found;
+    return APJ_OK;
+}
+extern "C" int apj_slab_spatial_correlations(apj_engine* e, double cutoff, int64_t n_ext, const double* ext6, const int32_t* ext_row,
+                                             double* counts, double* ori, double* vel, double* pair) {
+    APJ_NEED_STATE("apj_slab_spatial_correlations");
+    if (!e->st.slab || !(cutoff > 0) || !counts || !ori || !vel || !pair || n_ext < 0 || (n_ext > 0 && (!ext6 || !ext_row))) return APJ_E_INVALID;
+    if (std::fmod(cutoff, 2.0) != 0.0) return fail(e, APJ_E_INVALID, "apj_slab_spatial_correlations: cutoff must be a multiple of dr_c = 2");
+    if (int rc = pull_ctl(e)) return rc;
+    const SysCtl& c = e->hctl[0];
+    if (e->st.nranks > 1) {
+        // a pair must be seen by exactly one rank: from its left particle, across ONE slab edge
+        const double width = c.ncols * c.lp, need = (e->st.nranks == 2 ? 2.0 : 1.0) * cutoff + c.lp;
+        if (width < need) return fail(e, APJ_E_INVALID, "apj_slab_spatial_correlations: slabs narrower than the cutoff (+ one cell; twice the cutoff on 2 ranks): "
+                                                        "gather the box into a periodic handle for this cutoff");
+    }
+    APJ_OBS(apj_obs_spatial(&e->obs, e->st, e->stream, &e->launches, e->hctl.data(), cutoff, counts, ori, vel, pair, e->allocs,
+                            e->st.nranks > 1 ? n_ext : 0, ext6, reinterpret_cast<const int*>(ext_row)));
 }
 extern "C" int apj_vel_hist(apj_engine* e, const double* dv, int64_t* hist100) {
     APJ_NEED_STATE("apj_vel_hist");

@@ -119,16 +119,59 @@ __global__ void __launch_bounds__(OB) apj_occupancy_kernel(const DevState st, un
 // Correlations::spatialCorrelations accumulation (Correlations.h:85-152). Each unordered pair
 // whose separation can fall inside a bin is visited once (from the particle with the lower
 // position in cell order), over the distinct cells within `reach` of the particle's cell.
+// On a slab handle (several ranks) the columns are the rank's own: no wrap in x, pairs that cross the slab's right
+// edge are the business of apj_spatial_ext_kernel below.
+// One pair. The three correlation histograms have few, wide bins (dr_c = 2: 10 bins at the local cutoff 20), so a
+// block's threads would all hammer the same few shared-memory words: with PRIV every THREAD owns its copy of those
+// bins, laid out [bin][thread] (bank = thread: conflict-free, no atomics), folded over the block at the end. The
+// g(r) histogram has 20 x as many bins and stays one shared copy with atomics. Without PRIV (cutoff 140: 70 bins
+// per thread would not fit) everything is the shared copy.
+template <bool PRIV>
+__device__ __forceinline__ void corr_pair(double* sh, double* priv, const int nc, const int np, const double r, const double2 mcs, const double2 cj,
+                                          const double2 vi, const double spi, const double2 vj) {
+    const double dr_c = 2.0, dr_p = 0.1;   // Correlations.h:52-53
+    const double qp = floor(r / dr_p), qc = floor(r / dr_c);
+    if (qp < (double)np) atomicAdd(&sh[3 * nc + (int)qp], 1.0 / r);
+    if (qc < (double)nc) {
+        const int bin = (int)qc;
+        const double o = mcs.x * cj.x + mcs.y * cj.y;
+        const double v = (vi.x * vj.x + vi.y * vj.y) / (spi * sqrt(vj.x * vj.x + vj.y * vj.y));
+        if (PRIV) {
+            double* q = priv + (size_t)(3 * bin) * OB;
+            q[0] += 1.0; q[OB] += o; q[2 * OB] += v;
+        } else {
+            atomicAdd(&sh[bin], 1.0);
+            atomicAdd(&sh[nc + bin], o);
+            atomicAdd(&sh[2 * nc + bin], v);
+        }
+    }
+}
+// fold the per-thread copies into the block's shared copy (fixed order: lanes in a shuffle tree, warps by atomics of
+// whole-warp sums -- the cross-block order is that of the global atomics either way)
+__device__ __forceinline__ void corr_fold_private(double* sh, const double* priv_base, const int nc) {
+    for (int k = 0; k < 3 * nc; k++) {
+        double a = priv_base[(size_t)k * OB + threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        const int bin = k / 3, which = k - 3 * bin;
+        if ((threadIdx.x & 31) == 0 && a != 0.0) atomicAdd(&sh[which * nc + bin], a);
+    }
+}
+template <bool PRIV>
 __global__ void __launch_bounds__(OB) apj_spatial_kernel(const DevState st, const int bps, const int nc, const int np,
                                                          const int reach_scale, double* __restrict__ acc) {
-    extern __shared__ double sh[];  // counts[nc] | ori[nc] | vel[nc] | pair[np]
+    extern __shared__ double sh[];  // counts[nc] | ori[nc] | vel[nc] | pair[np] | PRIV: [3 nc][OB] per-thread copies
     const int sys = blockIdx.x / bps, blk = blockIdx.x - sys * bps;
     const SysCtl* __restrict__ ctl = st.ctl + sys;
     const int nb = 3 * nc + np;
     for (int k = threadIdx.x; k < nb; k += OB) sh[k] = 0.0;
+    double* priv_base = sh + ((nb + 1) & ~1);
+    double* priv = priv_base + threadIdx.x;
+    if (PRIV) for (int k = 0; k < 3 * nc; k++) priv[(size_t)k * OB] = 0.0;
     __syncthreads();
-    const double dr_c = 2.0, dr_p = 0.1;   // Correlations.h:52-53
-    const int b = ctl->b;
+    const double dr_c = 2.0, dr_p = 0.1;
+    const int b = ctl->b, w = ctl->ncols;
+    const bool clip = st.slab && st.nranks > 1;                  // own columns only, no wrap in x
     const double L = ctl->L, Lh = ctl->Lover2;
     const double rmax = fmax(nc * dr_c, np * dr_p);
     int reach = (int)floor(rmax / ctl->lp) + 1;
@@ -139,17 +182,19 @@ __global__ void __launch_bounds__(OB) apj_spatial_kernel(const DevState st, cons
     const int* __restrict__ start = st.cell_start + ctl->cell_base;
     const int* __restrict__ box = st.BOX[ctl->gen];
     const int i = blk * OB + threadIdx.x;
-    if (i < st.N) {
-        const long long g = (long long)sys * st.N + i;
+    if (i < ctl->n_own) {
+        const long long g = (long long)ctl->p0 + i;
         const double2 me = P[g];
         const double2 mcs = CSv[g];
         const double2 vi = V[g];
         const double spi = sqrt(vi.x * vi.x + vi.y * vi.y);
         const int c = box[g];
         const int cx = c / b, cy = c - cx * b;
-        for (int ox = 0; ox < span; ox++) {
-            int col = (span == b) ? ox : cx - reach + ox;
-            col %= b; if (col < 0) col += b;
+        const int xspan = clip ? 2 * reach + 1 : span;
+        for (int ox = 0; ox < xspan; ox++) {
+            int col = (!clip && span == b) ? ox : cx - reach + ox;
+            if (clip) { if (col < 0 || col >= w) continue; }
+            else { col %= b; if (col < 0) col += b; }
             for (int oy = 0; oy < span; oy++) {
                 int row = (span == b) ? oy : cy - reach + oy;
                 row %= b; if (row < 0) row += b;
@@ -158,22 +203,76 @@ __global__ void __launch_bounds__(OB) apj_spatial_kernel(const DevState st, cons
                 for (int j = max(start[cc], (int)g + 1); j < j1; j++) {
                     const double2 pj = P[j];
                     const double dx = apj_wrap1(pj.x - me.x, L, Lh), dy = apj_wrap1(pj.y - me.y, L, Lh);
-                    const double r = sqrt(apj_d2(dx, dy));
-                    const double qp = floor(r / dr_p), qc = floor(r / dr_c);
-                    if (qp < (double)np) atomicAdd(&sh[3 * nc + (int)qp], 1.0 / r);
-                    if (qc < (double)nc) {
-                        const int bin = (int)qc;
-                        const double2 vj = V[j];
-                        atomicAdd(&sh[bin], 1.0);
-                        { const double2 cj = CSv[j]; atomicAdd(&sh[nc + bin], mcs.x * cj.x + mcs.y * cj.y); }
-                        atomicAdd(&sh[2 * nc + bin], (vi.x * vj.x + vi.y * vj.y) / (spi * sqrt(vj.x * vj.x + vj.y * vj.y)));
-                    }
+                    corr_pair<PRIV>(sh, priv, nc, np, sqrt(apj_d2(dx, dy)), mcs, CSv[j], vi, spi, V[j]);
+                }
+            }
+        }
+    }
+    (void)reach_scale;
+    __syncthreads();
+    if (PRIV) { corr_fold_private(sh, priv_base, nc); __syncthreads(); }
+    for (int k = threadIdx.x; k < nb; k += OB) if (sh[k] != 0.0) atomicAdd(&acc[(size_t)sys * nb + k], sh[k]);
+}
+
+// Slab mode: pairs between an owned particle and an EXTERNAL one -- the particles of the rank(s) to the right that lie
+// within the cutoff of this slab's right edge, handed in by the caller sorted by cell row (ext_row[b+1]); planes
+// x | y | cos | sin | vx | vy of n_ext values each. Every such pair is counted here and nowhere else.
+__global__ void __launch_bounds__(OB) apj_spatial_ext_kernel(const DevState st, const int nc, const int np, const long long n_ext,
+                                                             const double* __restrict__ ext, const int* __restrict__ ext_row,
+                                                             double* __restrict__ acc) {
+    extern __shared__ double sh[];
+    const SysCtl* __restrict__ ctl = st.ctl;
+    const int nb = 3 * nc + np;
+    for (int k = threadIdx.x; k < nb; k += OB) sh[k] = 0.0;
+    __syncthreads();
+    const int b = ctl->b;
+    const double L = ctl->L, Lh = ctl->Lover2, lp = ctl->lp;
+    const double rmax = fmax(nc * 2.0, np * 0.1);
+    const int reach = (int)floor(rmax / lp) + 1;
+    const int span = (2 * reach + 1 >= b) ? b : 2 * reach + 1;
+    const double x_edge = -Lh + (double)(ctl->col0 + ctl->ncols) * lp;     // right edge of the slab
+    const int i = blockIdx.x * OB + threadIdx.x;
+    if (i < ctl->n_own) {
+        const long long g = (long long)ctl->p0 + i;
+        const double2 me = st.XY[ctl->cur][g];
+        if (x_edge - me.x < rmax + lp) {                                    // near enough to the edge to reach across it
+            const double2 mcs = st.CS[ctl->cur][g];
+            const double2 vi = st.V[ctl->gen][g];
+            const double spi = sqrt(vi.x * vi.x + vi.y * vi.y);
+            const int c = st.BOX[ctl->gen][g];
+            const int cy = c - (c / b) * b;
+            const double *ex = ext, *ey = ext + n_ext, *ec = ext + 2 * n_ext, *es = ext + 3 * n_ext, *evx = ext + 4 * n_ext, *evy = ext + 5 * n_ext;
+            for (int oy = 0; oy < span; oy++) {
+                int row = (span == b) ? oy : cy - reach + oy;
+                row %= b; if (row < 0) row += b;
+                for (int j = ext_row[row]; j < ext_row[row + 1]; j++) {
+                    const double dx = apj_wrap1(ex[j] - me.x, L, Lh), dy = apj_wrap1(ey[j] - me.y, L, Lh);
+                    corr_pair<false>(sh, nullptr, nc, np, sqrt(apj_d2(dx, dy)), mcs, make_double2(ec[j], es[j]), vi, spi, make_double2(evx[j], evy[j]));
                 }
             }
         }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < nb; k += OB) if (sh[k] != 0.0) atomicAdd(&acc[(size_t)sys * nb + k], sh[k]);
+    for (int k = threadIdx.x; k < nb; k += OB) if (sh[k] != 0.0) atomicAdd(&acc[k], sh[k]);
+}
+
+// owned particles within `width` of the slab's LEFT edge, compacted (order irrelevant): what the left neighbour
+// needs as its external set. out = 6 planes of `cap` values; *count receives the number found (may exceed cap).
+__global__ void __launch_bounds__(OB) apj_export_edge_kernel(const DevState st, const double width, const long long cap, double* __restrict__ out,
+                                                             int* __restrict__ count) {
+    const SysCtl* __restrict__ ctl = st.ctl;
+    const double x_left = -ctl->Lover2 + (double)ctl->col0 * ctl->lp;
+    for (int i = blockIdx.x * OB + threadIdx.x; i < ctl->n_own; i += gridDim.x * OB) {
+        const long long g = (long long)ctl->p0 + i;
+        const double2 p = st.XY[ctl->cur][g];
+        if (p.x - x_left < width) {
+            const int k = atomicAdd(count, 1);
+            if (k < cap) {
+                const double2 cs = st.CS[ctl->cur][g], v = st.V[ctl->gen][g];
+                out[k] = p.x; out[cap + k] = p.y; out[2 * cap + k] = cs.x; out[3 * cap + k] = cs.y; out[4 * cap + k] = v.x; out[5 * cap + k] = v.y;
+            }
+        }
+    }
 }
 
 // queue one two-level reduction on the stream; its 2 * n_sys raw sums land in d_dst (no host synchronisation)
@@ -292,8 +391,50 @@ int apj_obs_occupancy(ApjObsScratch* o, const DevState& st, cudaStream_t s, long
     for (int k = 0; k < st.n_sys; k++) for (int q = 0; q < 50; q++) hist50[50 * k + q] = (int64_t)h[128 * (size_t)k + q];
     return 0;
 }
+int apj_obs_export_edge(const DevState& st, cudaStream_t s, long long* launches, double width, long long cap, double* h_out6, long long* n_found) {
+    double* d = nullptr; int* dc = nullptr;
+    if (cudaMalloc(&d, sizeof(double) * 6 * (size_t)std::max<long long>(cap, 1)) != cudaSuccess) return APJ_E_CUDA_OBS;
+    if (cudaMalloc(&dc, sizeof(int)) != cudaSuccess) { cudaFree(d); return APJ_E_CUDA_OBS; }
+    cudaMemsetAsync(dc, 0, sizeof(int), s);
+    apj_export_edge_kernel<<<148 * 4, OB, 0, s>>>(st, width, cap, d, dc);
+    if (launches) *launches += 1;
+    int n = 0;
+    bool ok = cudaMemcpyAsync(&n, dc, sizeof(int), cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess;
+    if (ok && n <= cap && n > 0 && h_out6) {
+        for (int k = 0; k < 6 && ok; k++)          // compact the planes from stride cap to stride n
+            ok = cudaMemcpyAsync(h_out6 + (size_t)k * n, d + (size_t)k * cap, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+    }
+    cudaFree(d); cudaFree(dc);
+    *n_found = n;
+    return ok ? 0 : APJ_E_CUDA_OBS;
+}
+
+int apj_obs_spatial_ext(ApjObsScratch* o, const DevState& st, cudaStream_t s, long long* launches, double cutoff, long long n_ext,
+                        const double* h_ext6, const int* h_ext_row, int b, double* d_acc_row) {
+    (void)o;
+    if (n_ext <= 0) return 0;
+    const int np = (int)std::ceil(cutoff / 0.1), nc = (int)std::ceil(cutoff / 2.0);
+    const size_t nb = 3 * (size_t)nc + np;
+    double* d = nullptr; int* dr = nullptr;
+    if (cudaMalloc(&d, sizeof(double) * 6 * (size_t)n_ext) != cudaSuccess) return APJ_E_CUDA_OBS;
+    if (cudaMalloc(&dr, sizeof(int) * (size_t)(b + 1)) != cudaSuccess) { cudaFree(d); return APJ_E_CUDA_OBS; }
+    bool ok = cudaMemcpyAsync(d, h_ext6, sizeof(double) * 6 * (size_t)n_ext, cudaMemcpyHostToDevice, s) == cudaSuccess &&
+              cudaMemcpyAsync(dr, h_ext_row, sizeof(int) * (size_t)(b + 1), cudaMemcpyHostToDevice, s) == cudaSuccess;
+    if (ok) {
+        const size_t smem = nb * sizeof(double);
+        if (smem > 48 * 1024) apj_allow_max_smem(apj_spatial_ext_kernel);
+        apj_spatial_ext_kernel<<<(unsigned)((st.cap + OB - 1) / OB), OB, smem, s>>>(st, nc, np, n_ext, d, dr, d_acc_row);
+        if (launches) *launches += 1;
+        ok = cudaStreamSynchronize(s) == cudaSuccess;
+    }
+    cudaFree(d); cudaFree(dr);
+    return ok ? 0 : APJ_E_CUDA_OBS;
+}
+
 int apj_obs_spatial(ApjObsScratch* o, const DevState& st, cudaStream_t s, long long* launches, const SysCtl* hctl, double cutoff,
-                    double* counts, double* ori, double* vel, double* pair, std::vector<void*>& allocs) {
+                    double* counts, double* ori, double* vel, double* pair, std::vector<void*>& allocs,
+                    long long n_ext, const double* h_ext6, const int* h_ext_row) {
     (void)hctl;
     const int np = (int)std::ceil(cutoff / 0.1), nc = (int)std::ceil(cutoff / 2.0);   // Correlations.h:55-56
     const size_t nb = 3 * (size_t)nc + np, need = nb * st.n_sys;
@@ -310,11 +451,18 @@ int apj_obs_spatial(ApjObsScratch* o, const DevState& st, cudaStream_t s, long l
         o->d_corr = (double*)p; o->corr_cap = need;
     }
     cudaMemsetAsync(o->d_corr, 0, need * sizeof(double), s);
-    const int bps = (st.N + OB - 1) / OB;
-    const size_t smem = nb * sizeof(double);
-    if (smem > 48 * 1024) apj_allow_max_smem(apj_spatial_kernel);
-    apj_spatial_kernel<<<st.n_sys * bps, OB, smem, s>>>(st, bps, nc, np, 0, o->d_corr);
+    const int bps = (st.cap + OB - 1) / OB;
+    const bool priv = nc <= 16;                               // per-thread copies of the wide bins fit shared memory
+    const size_t smem = (((nb + 1) & ~(size_t)1) + (priv ? (size_t)3 * nc * OB : 0)) * sizeof(double);
+    if (priv) {
+        if (smem > 48 * 1024) apj_allow_max_smem(apj_spatial_kernel<true>);
+        apj_spatial_kernel<true><<<st.n_sys * bps, OB, smem, s>>>(st, bps, nc, np, 0, o->d_corr);
+    } else {
+        if (smem > 48 * 1024) apj_allow_max_smem(apj_spatial_kernel<false>);
+        apj_spatial_kernel<false><<<st.n_sys * bps, OB, smem, s>>>(st, bps, nc, np, 0, o->d_corr);
+    }
     if (launches) *launches += 1;
+    if (n_ext > 0) if (int rc = apj_obs_spatial_ext(o, st, s, launches, cutoff, n_ext, h_ext6, h_ext_row, hctl[0].b, o->d_corr)) return rc;
     std::vector<double> h(need);
     if (cudaMemcpyAsync(h.data(), o->d_corr, need * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) return APJ_E_CUDA_OBS;
     if (cudaStreamSynchronize(s) != cudaSuccess) return APJ_E_CUDA_OBS;

@@ -29,4 +29,6 @@ int apj_obs_occupancy(ApjObsScratch* o, const DevState& st, cudaStream_t s, long
 int apj_obs_enqueue_ring(ApjObsScratch* o, const DevState& st, cudaStream_t s, long long* launches, int kind, const double* h_param, long long* ticket);
 int apj_obs_fetch_ring(ApjObsScratch* o, const DevState& st, cudaStream_t s, long long first, long long count, double* h_out);
 int apj_obs_spatial(ApjObsScratch* o, const DevState& st, cudaStream_t s, long long* launches, const SysCtl* hctl, double cutoff,
-                    double* counts, double* ori, double* vel, double* pair, std::vector<void*>& allocs);
+                    double* counts, double* ori, double* vel, double* pair, std::vector<void*>& allocs,
+                    long long n_ext = 0, const double* h_ext6 = nullptr, const int* h_ext_row = nullptr);
+int apj_obs_export_edge(const DevState& st, cudaStream_t s, long long* launches, double width, long long cap, double* h_out6, long long* n_found);

@@ -48,7 +48,7 @@ EXPORTS = ["apj_version", "apj_last_error", "apj_create", "apj_destroy", "apj_se
            "apj_occupancy_hist", "apj_timer_begin", "apj_timer_end", "apj_time_step_kernel", "apj_time_step_parts",
            # slab mode (bound in slab.py)
            "apj_slab_create", "apj_slab_info", "apj_slab_export", "apj_slab_connect", "apj_slab_set_timeout", "apj_slab_ready",
-           "apj_slab_upload", "apj_slab_download", "apj_slab_get_pairs"]
+           "apj_slab_upload", "apj_slab_download", "apj_slab_get_pairs", "apj_slab_export_edge", "apj_slab_spatial_correlations"]
 
 _lib = None
 

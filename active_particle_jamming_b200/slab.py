@@ -33,6 +33,8 @@ def _bind(L):
     L.apj_slab_upload.argtypes = [C.c_void_p, C.POINTER(_State), _ip, C.c_int64]
     L.apj_slab_download.argtypes = [C.c_void_p, C.POINTER(_State), _ip, C.c_int64, _lp]
     L.apj_slab_get_pairs.argtypes = [C.c_void_p, _ip, C.c_int64, _lp]
+    L.apj_slab_export_edge.argtypes = [C.c_void_p, C.c_double, C.c_int64, _dp, _lp]
+    L.apj_slab_spatial_correlations.argtypes = [C.c_void_p, C.c_double, C.c_int64, _dp, _ip, _dp, _dp, _dp, _dp]
     L._slab_bound = True
     return L
 
@@ -165,6 +167,31 @@ class SlabRank(DeviceEngine):
         self._chk(self.lib.apj_slab_get_pairs(self.h, _p(p, _ip), tot.value, C.byref(tot)))
         return p[:tot.value]
 
+    def export_edge(self, width):
+        """(6, n) array x | y | cos | sin | vx | vy of the owned particles within `width` of this slab's left edge."""
+        n = C.c_int64(0)
+        self._chk(self.lib.apj_slab_export_edge(self.h, float(width), 0, None, C.byref(n)))
+        out = np.zeros((6, max(n.value, 1)))
+        if n.value:
+            self._chk(self.lib.apj_slab_export_edge(self.h, float(width), n.value, _p(out), C.byref(n)))
+        return out[:, :n.value]
+
+    def spatial_correlations_share(self, cutoff, ext):
+        """This rank's share of the raw correlation sums; `ext` = export_edge(cutoff) of the rank to the right."""
+        nc, npb = int(np.ceil(cutoff / 2.0)), int(np.ceil(cutoff / 0.1))
+        g = self.geometry()
+        b, lp, Lh = g["b"], g["lp"], g["Lover2"]
+        ext = np.asarray(ext, dtype=np.float64).reshape(6, -1)
+        row = np.clip(np.floor((ext[1] + Lh) / lp).astype(np.int64), 0, b - 1)      # cell row of every edge particle
+        order = np.argsort(row, kind="stable")
+        ext = np.ascontiguousarray(ext[:, order])
+        row_start = np.zeros(b + 1, dtype=np.int32)
+        row_start[1:] = np.cumsum(np.bincount(row, minlength=b))
+        cnt, ori, vel, pair = np.zeros(nc), np.zeros(nc), np.zeros(nc), np.zeros(npb)
+        self._chk(self.lib.apj_slab_spatial_correlations(self.h, float(cutoff), ext.shape[1], _p(ext), _p(row_start, _ip),
+                                                         _p(cnt), _p(ori), _p(vel), _p(pair)))
+        return np.concatenate([cnt, ori, vel, pair])
+
     # periodic-box entry points that have a slab counterpart
     def upload(self, **fields):
         raise ApjError(-4, "slab rank: use upload_local (or SlabBox / DistSlab .upload)")
@@ -273,6 +300,16 @@ class _SlabFront:
     def occupancy_hist(self):
         return self._allsum(sum(r.occupancy_hist() for r in self.local).astype(np.float64)).astype(np.int64)
 
+    def spatial_correlations(self, cutoff):
+        """Correlations::spatialCorrelations raw sums of the whole box (same dict as DeviceEngine.spatial_correlations):
+        every rank hands the particles near its left edge to its left neighbour, counts its own pairs and the pairs
+        that cross its right edge, and the shares are added."""
+        nc = int(np.ceil(cutoff / 2.0))
+        edges = self._exchange_edges(cutoff)            # per local rank: edge set of the rank to its right
+        shares = self._each_indexed(lambda k, r: r.spatial_correlations_share(cutoff, edges[k]))
+        tot = self._allsum(np.sum(shares, axis=0))
+        return dict(counts=tot[None, :nc], ori_sum=tot[None, nc:2 * nc], vel_sum=tot[None, 2 * nc:3 * nc], pair_sum=tot[None, 3 * nc:])
+
     def list_stats(self):
         s = self._allsum(np.array([float(sum(r.list_stats()[0] for r in self.local))]))
         return float(s[0]) / self.n, max(r.list_stats()[1] for r in self.local)
@@ -305,6 +342,13 @@ class SlabBox(_SlabFront):
 
     def _allsum(self, a):
         return np.asarray(a, dtype=np.float64)
+
+    def _each_indexed(self, fn):
+        return list(self.pool.map(lambda kr: fn(*kr), enumerate(self.local)))
+
+    def _exchange_edges(self, width):
+        mine = self._each(lambda r: r.export_edge(width))
+        return [mine[(k + 1) % self.nranks] for k in range(self.nranks)]
 
     def download(self, fields=None):
         fields = list(fields) if fields is not None else STATE_FIELDS + ["box"]
@@ -347,6 +391,27 @@ class DistSlab(_SlabFront):
     def _each(self, fn):
         self.dist.barrier()          # ranks enter a collective call together (bounded device-side waits)
         return [fn(self.local[0])]
+
+    def _each_indexed(self, fn):
+        self.dist.barrier()
+        return [fn(0, self.local[0])]
+
+    def _exchange_edges(self, width):
+        """My left-edge particles go to the rank on my left; I receive those of the rank on my right."""
+        torch, dist = self.torch, self.dist
+        mine = self.local[0].export_edge(width)
+        if self.nranks == 1:
+            return [mine]
+        left, right = (self.rank - 1) % self.nranks, (self.rank + 1) % self.nranks
+        dev = torch.device("cuda", self.device) if self.cuda else torch.device("cpu")
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.nranks)]
+        dist.all_gather(counts, torch.tensor([mine.shape[1]], dtype=torch.int64, device=dev))
+        send = torch.as_tensor(np.ascontiguousarray(mine)).to(dev)
+        recv = torch.zeros((6, int(counts[right].item())), dtype=torch.float64, device=dev)
+        ops = [dist.P2POp(dist.isend, send, left), dist.P2POp(dist.irecv, recv, right)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        return [recv.cpu().numpy()]
 
     def _allsum(self, a):
         t = self.torch.as_tensor(np.asarray(a, dtype=np.float64))

@@ -261,6 +261,18 @@ int apj_slab_download(apj_engine* e, apj_state* host, int32_t* ids, int64_t cap,
 /* Pairs (id_i, id_j), id_j > id_i, of the owned particles' Verlet lists including ghost partners: the
  * union over ranks is the reference's half-list pair set (each pair exactly once). pairs[2*cap]. */
 int apj_slab_get_pairs(apj_engine* e, int32_t* pairs, int64_t cap_pairs, int64_t* total);
+/* Correlations::spatialCorrelations (classes/Correlations.h:71-152) on the decomposed box. Pairs among a rank's own
+ * particles are its own; a pair that crosses a slab edge is counted by the rank of its LEFT particle, which needs the
+ * neighbour's particles within the cutoff of the shared edge:
+ *   apj_slab_export_edge           the owned particles within `width` of this slab's LEFT edge: 6 planes x | y | cos |
+ *                                  sin | vx | vy of *n values (call with cap = 0 to size the buffer);
+ *   apj_slab_spatial_correlations  this rank's additive share of the raw sums, given the edge set of the rank to its right
+ *                                  sorted by cell row, ext_row[b+1] = first particle of each row (b = cells per side).
+ * The host ships the edge sets between ranks (slab.py: torch.distributed plumbing, 10 x per run in the reference's
+ * cadence). Slabs must be wider than the cutoff + one cell (twice the cutoff on 2 ranks). */
+int apj_slab_export_edge(apj_engine* e, double width, int64_t cap, double* out6, int64_t* n);
+int apj_slab_spatial_correlations(apj_engine* e, double cutoff, int64_t n_ext, const double* ext6, const int32_t* ext_row,
+                                  double* counts, double* ori_sum, double* vel_sum, double* pair_sum);
 /* On a slab handle apj_step, apj_step_injected (noise indexed by global id), apj_force_rebuild and
  * apj_mark_origin are [collective]; apj_order_orientation (orient only), apj_msd, apj_fluct_area,
  * apj_vel_hist, apj_occupancy_hist and the COM left by apj_mark_origin are this rank's ADDITIVE share

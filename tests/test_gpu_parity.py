@@ -346,6 +346,7 @@ def test_remote_settings_correlations_cutoff_140():
     o, _ = relaxed_oracle(N, rho, seed=40, l_s=0.05, l_n=0.5, presteps=6)
     L = o.scalars()["L"]
     assert L / 2 > 140.0
+    o.assign(); o.build()        # as start() does before every spatialCorrelations (jamming.cpp:245-246): the boxPairs walk needs fresh cell lists
     vel, ori, pair = o.spatial_correlations(140.0)
     with device_from_state(o.state(), seed=1) as e:
         c = e.spatial_correlations(140.0)

@@ -89,4 +89,4 @@ def test_overlap_hue_is_the_references_integer(N, rho, lanes):
         got = e.overlap_hue()
     o.close()
     assert np.array_equal(got, want)
-    assert want.min() < 238 and want.max() == 240
+    assert want.min() < 236 and want.max() <= 240        # above jamming every particle overlaps; the int may go negative

@@ -127,6 +127,30 @@ def test_slab_mark_origin_and_relax_ramp():
         box.close()
 
 
+@pytest.mark.parametrize("nranks,cutoff", [(2, 20.0), (3, 20.0), (4, 60.0)])
+def test_slab_spatial_correlations_match_periodic(nranks, cutoff):
+    """Correlations::spatialCorrelations on the decomposed box (SURVEY 8e): own pairs + the pairs that cross a rank's
+    right edge (edge particles of the neighbour shipped by the host) add up to the periodic handle's raw sums --
+    the pair COUNTS exactly, the fp64 sums to summation-order rounding."""
+    N, rho = 65536, 0.9
+    o, _ = relaxed_oracle(N, rho, seed=90 + nranks, l_s=0.1, l_n=0.4, presteps=8)
+    s = o.state()
+    o.close()
+    with device_from_state(s, seed=3, lanes_per_particle=1, max_neighbors=64) as e:
+        want = e.spatial_correlations(cutoff)
+    box = slab_from_state(s, nranks, seed=3, lanes_per_particle=1, max_neighbors=64)
+    try:
+        got = box.spatial_correlations(cutoff)
+        assert np.array_equal(got["counts"], want["counts"])
+        for f in ("ori_sum", "vel_sum", "pair_sum"):
+            assert rel_err(got[f], want[f], floor=1.0) <= 1e-10, f
+        from active_particle_jamming_b200 import ApjError
+        with pytest.raises(ApjError):
+            box.spatial_correlations(400.0)                     # slabs narrower than the cutoff: refused, not miscounted
+    finally:
+        box.close()
+
+
 def test_slab_checkpoint_per_rank_files(tmp_path):
     """apj_save_checkpoint / apj_load_checkpoint on slab handles: every rank writes and reads its own share (no gather
     of the box). The restored box holds the stored bits, continues the Philox stream at the stored step and takes
