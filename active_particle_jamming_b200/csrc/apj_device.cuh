@@ -91,6 +91,11 @@ struct __align__(128) SysCtl {
     int kmin;        // lowest distance class the next launch must sweep (set when a launch swept too few; 0 after a commit)
     int slab_diag;   // first timed-out wait: (channel + 1) << 16 | mask of the ranks that had not arrived
     double skinD, skinDD;
+    // x_old can be reset WITHOUT a list build (start() :203 after relax: apj_mark_origin). The lists then are older than
+    // x_old; skinBase bounds the pair displacement between the list build and that reset (twice the largest COM-
+    // corrected displacement at the moment of the reset, accumulated over resets), so skinBase + D bounds it since the build.
+    double skinBase;
+    unsigned long long mark_d2;   // scratch of apj_mark_origin: bit pattern of the largest displacement^2 (atomicMax)
     long long n_retried;   // launches dropped because the sweep length chosen from the previous step's skinD was too short
     long long n_class[4];  // committed steps per swept class (APJ_CLASSES entries)
     unsigned long long seq[3];   // slab mode sequence numbers: step epochs, rebuild phase A, rebuild phase B
@@ -267,7 +272,7 @@ __device__ __forceinline__ int apj_class_for(double D, const DevState& st) {
 // over the blocks of a system: reads only fields no block writes before the commit)
 __device__ __forceinline__ int apj_sweep_class(const SysCtl* ctl, const DevState& st) {
     if (!st.truncate || !ctl->trunc_ok) return APJ_CLASSES - 1;
-    const int k = apj_class_for(ctl->skinD + 2.0 * ctl->skinDD + 0.01, st);
+    const int k = apj_class_for(ctl->skinBase + ctl->skinD + 2.0 * ctl->skinDD + 0.01, st);
     return k > ctl->kmin ? k : ctl->kmin;
 }
 

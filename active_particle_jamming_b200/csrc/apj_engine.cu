@@ -703,6 +703,16 @@ __global__ void apj_mark_origin_kernel(const DevState st) {
     const SysCtl* ctl = st.ctl + (int)(g / st.cap);
     if (g - ctl->p0 >= ctl->n_own) return;
     const double2 x = st.XY[ctl->cur][g];
+    {   // how far this particle has moved since the lists were built (COM drift removed, as newSkinList measures it):
+        // the largest value over the system feeds SysCtl::skinBase
+        const double2 xo = st.XO[ctl->gen][g];
+        const double ddx = apj_delta_norm(((x.x - xo.x) - ctl->COM[0]) + ctl->COM_old[0], ctl->L, ctl->Lover2);
+        const double ddy = apj_delta_norm(((x.y - xo.y) - ctl->COM[1]) + ctl->COM_old[1], ctl->L, ctl->Lover2);
+        unsigned long long bits = (unsigned long long)__double_as_longlong(apj_d2(ddx, ddy));   // >= 0: bit patterns order like the values
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long b = __shfl_xor_sync(__activemask(), bits, o); bits = b > bits ? b : bits; }
+        if ((threadIdx.x & 31) == 0) atomicMax(const_cast<unsigned long long*>(&ctl->mark_d2), bits);
+    }
     st.XR[ctl->cur][g] = x;     // x_real = x   (jamming.cpp:193-196)
     st.X0[ctl->gen][g] = x;     // x0 = x
     st.XO[ctl->gen][g] = x;     // saveOldPositions (:203)
@@ -712,6 +722,9 @@ extern "C" int apj_mark_origin(apj_engine* e) {
     if (!e) return APJ_E_INVALID;
     if (!e->have_state) return fail(e, APJ_E_STATE, "apj_mark_origin: no state uploaded");
     DevState& st = e->st;
+    if (int rc = pull_ctl(e)) return rc;
+    for (auto& c : e->hctl) c.mark_d2 = 0ull;
+    if (int rc = push_ctl(e)) return rc;
     apj_mark_origin_kernel<<<(unsigned)((st.ntot + 255) / 256), 256, 0, e->stream>>>(st);
     e->launches++;
     // COM = mean(x_real) in the deterministic two-level order of the step kernel
@@ -722,7 +735,15 @@ extern "C" int apj_mark_origin(apj_engine* e) {
         SysCtl& c = e->hctl[s];
         c.COM[0] = com[2 * s]; c.COM[1] = com[2 * s + 1];
         c.COM0[0] = c.COM_old[0] = c.COM[0]; c.COM0[1] = c.COM_old[1] = c.COM[1];
-        c.trunc_ok = 0;   // x_old moved without a list build: full lists until the next skin-triggered rebuild
+        // x_old moved without a list build. Periodic handles keep the skin-aware sweep length alive: the pair displacement
+        // between the build and this reset is bounded by twice the largest displacement just measured (skinBase), the
+        // skin test restarts from zero. Slab ranks would need the maximum over all ranks to stay in lockstep: full
+        // lists there until the next skin-triggered rebuild.
+        double d2max;
+        memcpy(&d2max, &c.mark_d2, sizeof d2max);
+        if (st.slab) c.trunc_ok = 0;
+        else c.skinBase += 2.0 * std::sqrt(d2max) * (1.0 + 1e-12);
+        c.skinD = 0.0; c.skinDD = 0.0;
     }
     return push_ctl(e);
 }

@@ -656,6 +656,7 @@ __global__ void apj_finish_rebuild_kernel(const DevState st) {
     // skin-aware sweep length: valid only while x_old is the state the lists were built from
     ctl->trunc_ok = ctl->save_old ? 1 : 0;
     ctl->skinD = 0.0;
+    ctl->skinBase = 0.0;
     ctl->kmin = 0;
     ctl->save_old = 0;
     ctl->stale = 0;

@@ -203,8 +203,8 @@ __device__ __forceinline__ void apj_commit(SysCtl* __restrict__ ctl, const DevSt
         ctl->stale = 1;                      // lists too old for the state this step read:
         ctl->save_old = 1;                   // drop the speculative result, rebuild, re-run
         ctl->n_discarded += 1;
-    } else if (kcls < APJ_CLASSES - 1 && apj_class_for(D, st) > kcls) {
-        ctl->kmin = apj_class_for(D, st);   // swept too few classes for this state: drop the result, re-run longer
+    } else if (kcls < APJ_CLASSES - 1 && apj_class_for(ctl->skinBase + D, st) > kcls) {
+        ctl->kmin = apj_class_for(ctl->skinBase + D, st);   // swept too few classes for this state: drop the result, re-run longer
         ctl->n_retried += 1;
     } else {
         ctl->COM[0] = a.x / st.N;            // calculate_COM (jamming.cpp:761-774)

@@ -25,9 +25,9 @@ extern "C" {
 #define APJ_OK 0
 #define APJ_E_INVALID (-1)  /* bad argument */
 #define APJ_E_CUDA (-2)     /* CUDA runtime / driver error (message has the CUDA string) */
-#define APJ_E_OVERFLOW (-3) /* a Verlet list exceeded max_neighbors; recreate with a larger value */
+#define APJ_E_OVERFLOW (-3) /* a Verlet list longer than the 96 entries the layout holds, or a slab capacity exceeded */
 #define APJ_E_STATE (-4)    /* call not valid in the current state (e.g. no state uploaded) */
-#define APJ_E_NCCL (-5)     /* NCCL error (slab mode) */
+/* (-5 is unassigned: the slab data path runs on device-side peer stores over NVLink, not on NCCL -- see "slab mode") */
 
 typedef struct apj_engine apj_engine;
 
@@ -40,7 +40,7 @@ typedef struct apj_config {
     double rn;             /* 0 -> 2.8  (jamming.cpp:112) */
     double rs_factor;      /* 0 -> 1.5  (rs = 1.5*rn, jamming.cpp:113) */
     uint64_t seed;         /* Philox4x32-10 key */
-    int32_t max_neighbors; /* capacity of one full Verlet list; 0 -> 48 */
+    int32_t max_neighbors; /* INITIAL capacity of one full Verlet list; 0 -> 48. Grown on demand up to 96 (periodic handles) */
     int32_t steps_per_launch; /* speculative steps between rebuild checks; 0 -> 16 */
     int32_t flags;         /* APJ_FLAG_* */
     int32_t tile_slots;    /* shared-memory tile capacity of a work block, in particles; 0 -> adaptive (follows the largest tile) */
@@ -51,9 +51,10 @@ typedef struct apj_config {
 #define APJ_FLAG_NO_GRAPH 1  /* launch kernels directly instead of through a CUDA graph */
 #define APJ_FLAG_SPLIT_TAIL 2  /* end every step with the separate fold + commit kernel (default: systems of >= 4096 work blocks) */
 #define APJ_FLAG_FUSED_TAIL 4  /* ... or always fold + commit in the step kernel's last block (default: small systems) */
-#define APJ_FLAG_PERSIST 16    /* persistent form of the split-tail step kernel (one system): one resident wave of blocks, each walking
-                                * tiles blk, blk + grid, ... with the next descriptor prefetched. Bit-identical; measured 8 % SLOWER than
-                                * one block per tile on B200 at N = 16M, hence opt-in */
+#define APJ_FLAG_PERSIST 16    /* pipelined persistent form of the split-tail step kernel (one system): one resident wave of blocks, each
+                                * walking tiles blk, blk + grid, ...; the last warp to finish a sweep refills the tile buffer (TMA) under
+                                * the epilogue. Bit-identical positions; measured on a par with one block per tile on B200 at N = 16M
+                                * (DESIGN.md section 7), hence opt-in (env APJ_STEP_PIPE=1 forces it on for tuning runs) */
 #define APJ_FLAG_TINY_GRID 8   /* tests, with APJ_FLAG_PERSIST: only 3 blocks, so every block walks many tiles */
 
 /* Host view of the per-particle fields of `struct Cell` (classes/Cell.h:15-43), 2D. Any

@@ -476,8 +476,17 @@ def test_skin_aware_sweep_length_is_bit_identical_to_full_sweep(l_s, lanes):
         with device_from_state(s, seed=seed, lanes_per_particle=lanes) as e:
             e.set_sweep_truncation(on)
             e.step(steps)
+            # x_old reset WITHOUT a list build (start() :203): the shortening stays in force through it, the bound now
+            # being skinBase (pair displacement between the build and the reset) + the skin-test value since the reset
+            e.step(7); e.mark_origin()
+            mid = e.sweep_stats()
+            e.step(60)
+            st = e.sweep_stats()
+            assert not on or (mid["active"] and sum(st["steps_per_class"][:3]) > sum(mid["steps_per_class"][:3]))
+            e.step(steps - 67)
             st = e.sweep_stats()
             out.append((e.download(), e.counters(), st))
+    steps *= 2
     (a, ca, sa), (b, cb, sb) = out
     assert ca["step"] == cb["step"] == steps
     assert ca["resetCounter"] == cb["resetCounter"] and ca["resetCounter"] >= 2
