@@ -83,6 +83,9 @@ struct __align__(128) SysCtl {
     int n_end;       // scratch of the cell scan: p0 + particles binned into owned cells
     int col0, ncols; // slab mode: owned cell columns [col0, col0 + ncols) of the global b x b grid (periodic: 0, b)
     int last_col_start;  // first particle of the last owned column (index of the right neighbour's ghost copy)
+    int blk_shift;       // slab mode: work block the grid starts with (first block of the LAST owned column), so that the
+                         // blocks that push halo data to the neighbours run first and their system-scope fences are long
+                         // done when the launch drains; 0 otherwise
     int slab_err;    // sticky: 1 peer wait timed out, 2 migrant crossed more than one slab, 4 capacity exceeded
     // Skin-aware sweep length (see APJ_CLASSES below). skinD = sqrt(l1)+sqrt(l2) of newSkinList
     // (jamming.cpp:611) for the state the last committed step started from (0 right after a

@@ -304,6 +304,7 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     if (st.S > apj_max_list_capacity()) { e->err = "apj_create: max_neighbors too large (<= 96)"; return bail(APJ_E_INVALID); }
     // lanes per particle: spread small systems over enough warps to hide latency (measured on B200)
     st.G = cfg->lanes_per_particle;
+    if (const char* le = getenv("APJ_LANES")) if (st.G == 0) st.G = atoi(le);   // tuning runs
     if (st.G == 0) st.G = st.ntot < 150000 ? 4 : (st.ntot < 400000 ? 2 : 1);
     if (st.G != 1 && st.G != 2 && st.G != 4 && st.G != 8) { e->err = "apj_create: lanes_per_particle must be 1, 2, 4 or 8"; return bail(APJ_E_INVALID); }
 #ifndef APJ_TB_G1

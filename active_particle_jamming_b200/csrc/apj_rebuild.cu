@@ -425,6 +425,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) apj_make_tiles_kernel(const DevSta
         col_blk[w] = nblk;
         ctl->nblk = nblk;
         ctl->last_col_start = start[(w - 1) * b];
+        ctl->blk_shift = (st.slab && st.nranks > 1) ? col_blk[w - 1] : 0;
         ctl->tile_max = 0;
     }
 }

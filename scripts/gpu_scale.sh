@@ -16,7 +16,7 @@ python - <<PY
 import json, glob
 for f in sorted(glob.glob("${O}_n*.json") + glob.glob("${O}_pipe_n*.json")):
     try:
-        d = json.load(open(f)); r = d["roofline"]
+        d = json.loads([l for l in open(f) if l.startswith("{")][-1]); r = d["roofline"]
         print(f.split("/")[-1], "gpus", d["n_gpus"], "value %.4e" % d["value"], "checksum", d["state_checksum"]["value"], "reset", d["state_checksum"]["resetCounter"],
               "kernel_ms %.4f" % r["kernel_ms"], "parts", {k: round(v, 4) for k, v in r["parts_ms"].items() if k != "how"}, "e2e %.3e" % (d.get("e2e") or {}).get("value", 0))
     except Exception as e:
