@@ -977,59 +977,6 @@ __global__ void __launch_bounds__(RC_TB) apj_reduce_commit_kernel(const DevState
     }
 }
 
-// The same fold for systems of <= RCS_MAX work blocks (1M particles; a slab of the 16M box on 8 GPUs): ONE block per
-// system, no ticket, no second level -- the two-level form above costs two dependent trips to memory and an atomic,
-// ~10 us that are 8-14 % of such a system's step. RCS_PER consecutive partials per thread, shuffle tree, warps in order.
-constexpr int RCS_TB = 1024, RCS_BATCH = 4, RCS_PER = 16, RCS_MAX = RCS_TB * RCS_PER;   // 16384 blocks = 4M particles
-__global__ void __launch_bounds__(RCS_TB) apj_reduce_commit_small_kernel(const DevState st) {
-    __shared__ double4 s_w[RCS_TB / 32];
-    const int sys = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    SysCtl* __restrict__ ctl = st.ctl + sys;
-    if (ctl->stale || ctl->step >= ctl->target) return;
-    const int nblk = st.persist_grid > 0 ? min(st.persist_grid, ctl->nblk) : ctl->nblk;
-    const double4* __restrict__ part = st.partials + (long long)sys * st.maxblk;
-    double4 a = make_double4(0.0, 0.0, 0.0, 0.0);
-    for (int k0 = t * RCS_PER; k0 < t * RCS_PER + RCS_PER && k0 < nblk; k0 += RCS_BATCH) {
-        double4 v[RCS_BATCH];
-#pragma unroll
-        for (int u = 0; u < RCS_BATCH; u++)              // a batch of loads in flight before the first use
-            v[u] = k0 + u < nblk ? rc_load(part + k0 + u) : make_double4(0.0, 0.0, 0.0, 0.0);
-#pragma unroll
-        for (int u = 0; u < RCS_BATCH; u++) { a.x += v[u].x; a.y += v[u].y; apj_top2_merge(a.z, a.w, v[u].z, v[u].w); }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
-        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
-        const double b1 = __shfl_xor_sync(0xffffffffu, a.z, o), b2 = __shfl_xor_sync(0xffffffffu, a.w, o);
-        apj_top2_merge(a.z, a.w, b1, b2);
-    }
-    if (lane == 0) s_w[wid] = a;
-    __syncthreads();
-    if (wid != 0) return;
-    a = s_w[lane];                                       // 32 warps: one more shuffle tree
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
-        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
-        const double b1 = __shfl_xor_sync(0xffffffffu, a.z, o), b2 = __shfl_xor_sync(0xffffffffu, a.w, o);
-        apj_top2_merge(a.z, a.w, b1, b2);
-    }
-    if (st.slab) {
-        const unsigned long long ep = ctl->seq[0];
-        if (lane < st.nranks) {
-            SlabMail* m = apj_peer(st, lane, st.mail);
-            m->part[ep & 1][st.rank] = a;
-            __threadfence_system();
-            apj_st_release_sys(&m->flag[0][st.rank], ep + 1);
-        }
-        __syncwarp();
-        apj_slab_commit_warp(st, ctl);
-        return;
-    }
-    if (lane == 0) apj_commit(ctl, st, a, apj_sweep_class(ctl, st));
-}
-
 // Slab mode: second half of the step. Waits for the partials of all ranks (pushed by their step
 // kernels, see above), folds them in rank order and takes the reference's decision
 // (jamming.cpp:611): commit the speculative step or drop it and rebuild. One warp.
@@ -1100,8 +1047,7 @@ void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int a
     if (G == 1 && st.split_tail) {
         if (st.persist_grid > 0) { launch_pipe<TB>(st, s, noise_by_id, always_full); apj_check_launch("apj_step_pipe_kernel"); }
         else { launch_variant<TB, 1, true>(st, s, noise_by_id, always_full); apj_check_launch("apj_step_kernel (split tail)"); }
-        if (st.maxblk <= RCS_MAX) apj_reduce_commit_small_kernel<<<st.n_sys, RCS_TB, 0, s>>>(st);
-        else apj_reduce_commit_kernel<<<dim3((st.maxblk + RC_CHUNK - 1) / RC_CHUNK, st.n_sys), RC_TB, 0, s>>>(st);
+        apj_reduce_commit_kernel<<<dim3((st.maxblk + RC_CHUNK - 1) / RC_CHUNK, st.n_sys), RC_TB, 0, s>>>(st);
         apj_check_launch("apj_reduce_commit_kernel");
     } else {
         launch_variant<TB, G, false>(st, s, noise_by_id, always_full);
@@ -1138,8 +1084,7 @@ static void launch_parts(const DevState& st, cudaStream_t s, void (*between)(int
         if (st.persist_grid > 0) launch_pipe<TB>(st, s, nullptr, 0);
         else launch_variant<TB, 1, true>(st, s, nullptr, 0);
         between(0, arg);
-        if (st.maxblk <= RCS_MAX) apj_reduce_commit_small_kernel<<<st.n_sys, RCS_TB, 0, s>>>(st);
-        else apj_reduce_commit_kernel<<<dim3((st.maxblk + RC_CHUNK - 1) / RC_CHUNK, st.n_sys), RC_TB, 0, s>>>(st);
+        apj_reduce_commit_kernel<<<dim3((st.maxblk + RC_CHUNK - 1) / RC_CHUNK, st.n_sys), RC_TB, 0, s>>>(st);
         between(1, arg);
     } else {
         launch_variant<TB, G, false>(st, s, nullptr, 0);
