@@ -143,12 +143,15 @@ static int build_group_graph(apj_engine* e);
 // when a rebuild produced a tile larger than the capacity (nothing was committed, the system is
 // still stale) or when a smaller capacity would fit one more block per SM.
 static int blocks_per_sm(const DevState& st, int cap) {
-    const size_t per_block = (size_t)(cap + 1) * 48 + (st.G > 1 ? (size_t)st.ppb * 32 : 0) + apj_step_extra_smem(st) + 1024 + 1024;
+    // dynamic + static shared memory of a step block + the 1 KB the driver reserves per resident block
+    const size_t per_block = (size_t)(cap + 1) * 48 + (st.G > 1 ? (size_t)st.ppb * 32 : 0) + apj_step_extra_smem(st) + 768 + 1024;
     const int by_smem = (int)((size_t)233472 / per_block);
     return std::max(1, std::min(by_smem, apj_step_blocks_per_sm_limit(st.tb)));   // register file: __launch_bounds__ of the step kernel
 }
 static int best_tile_cap(const DevState& st, int need) {
-    need = std::min(std::max(need + need / 32 + 8, 64), 4094);
+    // slack before a denser tile forces a re-launch: 3 % + 8 slots (APJ_TILE_SLACK=0, tuning runs: none)
+    static const int slack = getenv("APJ_TILE_SLACK") ? atoi(getenv("APJ_TILE_SLACK")) : 1;
+    need = std::min(std::max(slack ? need + need / 32 + 8 : need, 64), 4094);
     const int target = blocks_per_sm(st, need);
     int lo = need, hi = 4094;                                         // largest cap with the same block count
     while (lo < hi) {
@@ -305,7 +308,9 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     // lanes per particle: spread small systems over enough warps to hide latency (measured on B200)
     st.G = cfg->lanes_per_particle;
     if (const char* le = getenv("APJ_LANES")) if (st.G == 0) st.G = atoi(le);   // tuning runs
-    if (st.G == 0) st.G = st.ntot < 150000 ? 4 : (st.ntot < 400000 ? 2 : 1);
+    // measured on B200 (ms per step, lanes 1 / 2 / 4): N = 16 384: .0129 / .0128 / .0111; 65 536: .0158 / .0139 / .0188;
+    // 131 072: .0221 / .0209 / .0287; 262 144: .0359 / .0432 / .0569; 524 288: .0470 / .0648 / .0992
+    if (st.G == 0) st.G = st.ntot < 40000 ? 4 : (st.ntot < 200000 ? 2 : 1);
     if (st.G != 1 && st.G != 2 && st.G != 4 && st.G != 8) { e->err = "apj_create: lanes_per_particle must be 1, 2, 4 or 8"; return bail(APJ_E_INVALID); }
 #ifndef APJ_TB_G1
 #define APJ_TB_G1 256

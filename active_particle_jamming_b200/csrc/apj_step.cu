@@ -330,9 +330,24 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     for (int j = 0; j < QREG; j++) q[j] = (j < st.max_quads) ? __ldg(gq + (size_t)j * TB) : make_uint4(0u, 0u, 0u, 0u);
     const bool active = t < sd.n;                      // epilogue mapping: thread t <-> particle t
     const long long g = (long long)sd.g0 + (active ? t : 0);
+    // x_old / x_real are only needed at the very end of the epilogue. APJ_LATE_XO asks L2 for them here and loads them
+    // right after the sweep, which keeps 8 registers out of the sweep: measured +0.6 % at 64 registers / 4 blocks per SM,
+    // and the 48-register / 5-block build it was meant for gains only 3.6 % -- default: early.
+#ifndef APJ_LATE_XO
+#define APJ_EARLY_XO 1
+#endif
+#ifdef APJ_EARLY_XO
     double2 xo = make_double2(0.0, 0.0), xr = xo;
+#endif
     int id = 0;
-    if (t < PPB) { xo = st.XO[gen][g]; xr = st.XR[cur][g]; id = st.ID[gen][g]; }
+    if (t < PPB) {
+#ifdef APJ_EARLY_XO
+        xo = st.XO[gen][g]; xr = st.XR[cur][g];
+#else
+        apj_prefetch_l2(st.XO[gen] + g); apj_prefetch_l2(st.XR[cur] + g);
+#endif
+        id = st.ID[gen][g];
+    }
     const double L = ctl->L, Lh = ctl->Lover2;
     const double rn2 = st.rn2;
     // randuni() of this step (jamming.cpp:667): depends on (id, step) only, so it is drawn while the tile is in flight
@@ -399,18 +414,16 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
 
     double sum_x = 0.0, sum_y = 0.0, top1 = 0.0, top2 = 0.0;
     if (active) {
+#ifndef APJ_EARLY_XO
+        double2 xo, xr;                                // issued now, consumed at the end of the epilogue (L2 hits: prefetched in the head)
+        asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(xo.x), "=d"(xo.y) : "l"(st.XO[gen] + g));
+        asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(xr.x), "=d"(xr.y) : "l"(st.XR[cur] + g));
+#endif
         const unsigned own = (unsigned)(sd.own_slot + t) * 16u;
         const double2 me = lds_f64x2(sXY + own), mcs = lds_f64x2(sXY + dCS + own), mrr = lds_f64x2(sXY + dRR + own);
         const double Ri = mrr.x;
         double Fx = acc.Fx, Fy = acc.Fy, ax = acc.ax, ay = acc.ay;
         if (!ctl->no_self_once) { ax += mcs.x; ay += mcs.y; }  // self term: Cell::update left x_new = cosp (Cell.h:102-103)
-
-        // ---- newSkinList: displacement since the last rebuild, COM drift removed ----
-        {
-            const double ddx = apj_delta_norm(((me.x - xo.x) - ctl->COM[0]) + ctl->COM_old[0], L, Lh);
-            const double ddy = apj_delta_norm(((me.y - xo.y) - ctl->COM[1]) + ctl->COM_old[1], L, Lh);
-            top1 = apj_d2(ddx, ddy);
-        }
 
         // ---- phi = atan2(y_new, x_new) + CTnoise * randuni()   (jamming.cpp:667), then Cell::update:
         //      periodicAngles (single wrap, Cell.h:160-166), cosp = cos(phi), sinp = sin(phi) ----
@@ -428,12 +441,18 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         const double vx = Fx * mrr.y, vy = Fy * mrr.y;   // Rinv = 1/R stored at upload (jamming.cpp:298)
         const double dx = vx * st.dt, dy = vy * st.dt;
         double x = me.x + dx, y = me.y + dy;
-        const double xrn = xr.x + dx, yrn = xr.y + dy;
         if (x >= Lh) x -= L; else if (x < -Lh) x += L;   // Cell::PBC, single wrap (Cell.h:168-175)
         if (y >= Lh) y -= L; else if (y < -Lh) y += L;
 
         st.XY[cur ^ 1][g] = make_double2(x, y);
         st.CS[cur ^ 1][g] = make_double2(cs, sn);
+        // ---- newSkinList: displacement since the last rebuild, COM drift removed (of the state the step STARTED from) ----
+        {
+            const double ddx = apj_delta_norm(((me.x - xo.x) - ctl->COM[0]) + ctl->COM_old[0], L, Lh);
+            const double ddy = apj_delta_norm(((me.y - xo.y) - ctl->COM[1]) + ctl->COM_old[1], L, Lh);
+            top1 = apj_d2(ddx, ddy);
+        }
+        const double xrn = xr.x + dx, yrn = xr.y + dy;
         st.XR[cur ^ 1][g] = make_double2(xrn, yrn);
         if (SLAB) {   // halo exchange fused into the epilogue: boundary columns are stored straight into the
                       // neighbours' ghost slots (peer memory over NVLink), in the half they read next step

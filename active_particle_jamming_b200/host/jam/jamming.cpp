@@ -98,6 +98,7 @@ struct Engine
     double calculateOrderParameter();
     vector<double> calculateSystemOrientation();
     void print_video(Print&);
+    bool device_init = false;       // initCells ran on the device: `cell` is filled on demand only
     void film_hue();
     bool pulled_hue = false;
     double delta_norm(double);
@@ -207,6 +208,21 @@ Engine::~Engine()
 // offset-row lattice, random polarity (reference initCells :285-354, 2D branch).
 void Engine::initCells()
 {
+    // APJ_DEVICE_INIT=1 (or N >= 4M): the lattice is drawn on the device (apj_init_lattice, csrc/apj_setup.cu) and
+    // vector<Cell> stays empty until somebody asks for it (pull_cells): a 16M-particle run never builds ~5 GB of Cell
+    // records on the host. Only the box length is needed here (topology() and apj_create depend on it).
+    const char* di = getenv("APJ_DEVICE_INIT");
+    device_init = di ? atoi(di) != 0 : N >= 4194304;
+    if (device_init) {
+        const char* d = getenv("APJ_DEVICE");
+        if (apj_lattice_box_length(N, 1, g_seed, &dens, d ? atoi(d) : 0, &L) != APJ_OK) {
+            cout << "apj_lattice_box_length failed: " << apj_last_error(NULL) << endl;
+            exit(120);
+        }
+        Lover2 = L/2.0;
+        cell.clear();
+        return;
+    }
     cell.assign(N, Cell());
     double area = 0;
     for (int i = 0; i < N; i++) {
@@ -292,6 +308,19 @@ ApjBatch* Engine::attach_batch(vector<Engine*>& runs)
     if (rc != APJ_OK) { cout << "apj_create failed (" << rc << "): " << apj_last_error(NULL) << endl; exit(120); }
     b->check(apj_set_activity(b->dev, CF.data(), CT.data()), "apj_set_activity");
 
+    if (S == 1 && runs[0]->device_init) {      // Engine::initCells on the device: same seed as apj_lattice_box_length saw
+        b->check(apj_init_lattice(b->dev, g_seed), "apj_init_lattice");
+        double zero[2] = {0.0, 0.0};
+        b->check(apj_set_com(b->dev, 0, zero, zero, zero), "apj_set_com");
+        b->check(apj_skip_self_term_once(b->dev, 1), "apj_skip_self_term_once");
+        b->touch();
+        Engine* e = runs[0];
+        e->batch = b; e->dev = b->dev; e->sys = 0; e->lists_fresh = true;
+        if (e->fluct) e->bind_observers();
+        return b;
+    }
+    for (int s = 0; s < S; s++)
+        if (runs[s]->device_init) { cout << "APJ_DEVICE_INIT: batched sweeps initialise on the host" << endl; exit(120); }
     const size_t T = (size_t)S*N;
     vector<double> x(T), y(T), xr(T), yr(T), x0(T), y0(T), xo(T), yo(T), R(T), phi(T), cp(T), sp(T);
     vector<int32_t> box(T);
@@ -444,9 +473,14 @@ void Engine::pull_cells()
     s.x_old = f[6].data(); s.y_old = f[7].data(); s.R = f[8].data(); s.phi = f[9].data(); s.cosp = f[10].data(); s.sinp = f[11].data();
     s.vx = f[12].data(); s.vy = f[13].data(); s.box = box.data();
     check(apj_download_state(dev, &s), "apj_download_state");
+    if ((long)cell.size() != N) {                   // device-side initCells: the records exist from now on
+        cell.assign(N, Cell());
+        for (int i = 0; i < N; i++) { Cell& c = cell[i]; c.index = i; c.L = L; c.Lover2 = Lover2; c.dt = dt; c.theta = PI/2.0; c.over = 240; }
+    }
     for (int i = 0; i < N; i++) {
         Cell& c = cell[i];
         const size_t k = o + i;
+        c.R = f[8][k]; c.Rinv = 1.0/c.R;
         c.x[0] = f[0][k]; c.x[1] = f[1][k]; c.x_real[0] = f[2][k]; c.x_real[1] = f[3][k];
         c.x0[0] = f[4][k]; c.x0[1] = f[5][k]; c.x_old[0] = f[6][k]; c.x_old[1] = f[7][k];
         c.phi = f[9][k]; c.cosp = f[10][k]; c.sinp = f[11][k]; c.vx = f[12][k]; c.vy = f[13][k];
@@ -499,6 +533,10 @@ void Engine::film_hue()
     pending--;
     flush();
     pending = 1;
+    if ((long)cell.size() != N) {                   // device-side initCells: materialise the records (no stepping: pending is parked)
+        const long int keep = pending;
+        pending = 0; pull_cells(); pending = keep;
+    }
     vector<int32_t> hue((size_t)batch->nsys*N);
     check(apj_overlap_hue(dev, hue.data()), "apj_overlap_hue");
     for (int i = 0; i < N; i++) cell[i].over = hue[(size_t)sys*N + i];

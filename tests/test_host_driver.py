@@ -138,6 +138,37 @@ def test_video_frames_carry_the_overlap_hue(jam, tmp_path):
 
 
 @pytest.mark.gpu
+def test_device_side_init_runs_the_reference_cadence(jam, tmp_path):
+    """APJ_DEVICE_INIT=1 (default for N >= 4M): Engine::initCells runs on the device (apj_init_lattice), vector<Cell> is
+    never built for the run; the output tree, the cadence and the summary are those of a host-initialised run."""
+    N, steps = 2048, 400
+    outs = {}
+    for mode in ("0", "1"):
+        root = tmp_path / ("m" + mode)
+        os.makedirs(root)
+        env = dict(os.environ, APJ_OUTPUT_ROOT=str(root), APJ_SEED="11", APJ_DEVICE_INIT=mode, APJ_MAKEVID="1")
+        r = subprocess.run([jam, "di", "run0", str(N), str(steps), "0.1", "0.3", "0.9"], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[mode] = read_tree(os.path.join(str(root), "local_output", "di", "run0"))
+    a, b = outs["0"], outs["1"]
+    assert sorted(a) == sorted(b)
+    for name in a:
+        la, lb = a[name].split("\n"), b[name].split("\n")
+        assert len(la) == len(lb), name
+    def col(tree, name, k):
+        return np.array([float(l.split("\t")[k]) for l in tree[name].split("\n")[:-1]])
+    assert np.array_equal(col(a, "dat/order.dat", 0), col(b, "dat/order.dat", 0))                    # same time stamps
+    assert abs(col(a, "dat/order.dat", 1).mean() - col(b, "dat/order.dat", 1).mean()) < 0.25         # other random lattice, same physics
+    assert 0.3 < col(b, "dat/MSD.dat", 1)[-1] / col(a, "dat/MSD.dat", 1)[-1] < 3.0
+    sa, sb = a["dat/summary.dat"].split("\n"), b["dat/summary.dat"].split("\n")
+    assert sa[1] == sb[1] and sa[3] == sb[3]                                                        # N, steps + 1
+    frames = b["vid/ovito.txt"].split("\n")
+    assert frames[0] == str(N) and len(frames) - 1 == (steps // 100 + 1) * (N + 2)
+    radii = np.array([float(l.split("\t")[1]) for l in frames[2:N + 2]])
+    assert abs(radii.mean() - 1.0) < 0.02 and abs(radii.std() - 0.1) < 0.02                           # the records were materialised from the device
+
+
+@pytest.mark.gpu
 def test_engine_mirrors_expose_reference_state(tmp_path):
     """Cell / Box mirrors: pull_cells, pull_cell_lists, pull_verlet_lists give the reference's views."""
     prog = r'''
