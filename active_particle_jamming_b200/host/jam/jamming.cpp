@@ -675,6 +675,7 @@ static int run_sweep(const char* path, int per_batch)
         specs.push_back(r);
     }
     if (per_batch < 1) per_batch = 64;
+    int skipped = 0;
     size_t first = 0;
     while (first < specs.size()) {
         size_t last = first + 1;                          // consecutive lines of one shape form a batch
@@ -684,11 +685,24 @@ static int run_sweep(const char* path, int per_batch)
             const RunSpec& r = specs[k];
             gen.seed((uint32_t)(g_seed + 7919u*(uint64_t)r.line));       // every line its own initial condition
             normdist.reset();
+            // a bad line is reported and skipped on its own: it must not take the other replicas of its batch with it
+            if (r.n < 1 || r.steps < 1 || !(r.rho > 0)) {
+                cout << path << ":" << r.line << ": skipped (N, steps and rho must be positive)" << endl;
+                skipped++;
+                continue;
+            }
             Engine* e = new Engine(r.full, r.run, r.n, r.steps, r.l_s, r.l_n, r.rho);
             e->setup();
+            if (e->b < 3) {     // b = floor(L / 2 rn) < 3 aliases neighbour cells (reference :359): the device refuses such a box
+                cout << path << ":" << r.line << ": skipped (box too small: L = " << e->L << " gives b = " << e->b << " < 3 cells per side)" << endl;
+                delete e;
+                skipped++;
+                continue;
+            }
             e->open_outputs();
             runs.push_back(e);
         }
+        if (runs.empty()) { first = last; continue; }
         ApjBatch* b = Engine::attach_batch(runs);
         for (Engine* e : runs) { e->assignCellsToGrid(); e->buildVerletLists(); }
         Engine::relax_all(runs);
@@ -703,7 +717,8 @@ static int run_sweep(const char* path, int per_batch)
         delete b;
         first = last;
     }
-    return 0;
+    if (skipped) cout << skipped << " line(s) of " << path << " skipped" << endl;
+    return skipped ? 3 : 0;
 }
 
 int main(int argc, char* argv[])

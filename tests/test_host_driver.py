@@ -238,6 +238,21 @@ def test_sweep_runs_input_lines_as_batched_replicas(jam, tmp_path):
     assert abs(order["runA"] - order["runD"]) < 0.15                                 # same point, different batch: same physics
 
 
+@pytest.mark.gpu
+def test_sweep_skips_a_bad_line_instead_of_aborting_the_batch(jam, tmp_path):
+    """one impossible line (a box of fewer than 3 x 3 cells) used to exit(720) the whole per-GPU sweep
+    process. It is reported and skipped on its own; its batch mates run; the exit status says that lines were skipped."""
+    inp = tmp_path / "input.txt"
+    inp.write_text("sw good1 256 300 0.3 0.5 0.9\nsw tiny 16 300 0.3 0.5 0.9\nsw good2 256 300 0.3 0.5 0.9\nsw neg 256 300 0.3 0.5 -1\n")
+    env = dict(os.environ, APJ_OUTPUT_ROOT=str(tmp_path), APJ_SEED="5")
+    r = subprocess.run([jam, "--sweep", str(inp), "8"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 3, r.stdout + r.stderr
+    assert "input.txt:2: skipped (box too small" in r.stdout and "input.txt:4: skipped" in r.stdout and "2 line(s)" in r.stdout
+    for name in ("good1", "good2"):
+        assert os.path.exists(os.path.join(str(tmp_path), "local_output", "sw", name, "dat", "summary.dat"))
+    assert not os.path.exists(os.path.join(str(tmp_path), "local_output", "sw", "tiny"))
+
+
 def test_host_topology_and_lattice_match_the_reference_algorithm(tmp_path):
     """Engine::initCells / Engine::topology are host-side setup (no device): the grid (b, lp, the 3x3 periodic
     neighbour table in the reference's numbering, jamming.cpp:356-410) must equal the oracle's for the same L, and
