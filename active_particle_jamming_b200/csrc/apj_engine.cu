@@ -703,25 +703,31 @@ extern "C" int apj_get_com(apj_engine* e, int32_t s, double* com, double* com0, 
     return APJ_OK;
 }
 
-__global__ void apj_mark_origin_kernel(const DevState st) {
+__global__ void __launch_bounds__(256) apj_mark_origin_kernel(const DevState st) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= st.ntot) return;
-    const SysCtl* ctl = st.ctl + (int)(g / st.cap);
-    if (g - ctl->p0 >= ctl->n_own) return;
-    const double2 x = st.XY[ctl->cur][g];
-    {   // how far this particle has moved since the lists were built (COM drift removed, as newSkinList measures it):
+    const int sys = (int)(min(g, st.ntot - 1) / st.cap);
+    const SysCtl* ctl = st.ctl + sys;
+    unsigned long long bits = 0ull;
+    if (g < st.ntot && g - ctl->p0 < ctl->n_own) {
+        const double2 x = st.XY[ctl->cur][g];
+        // how far this particle has moved since the lists were built (COM drift removed, as newSkinList measures it):
         // the largest value over the system feeds SysCtl::skinBase
         const double2 xo = st.XO[ctl->gen][g];
         const double ddx = apj_delta_norm(((x.x - xo.x) - ctl->COM[0]) + ctl->COM_old[0], ctl->L, ctl->Lover2);
         const double ddy = apj_delta_norm(((x.y - xo.y) - ctl->COM[1]) + ctl->COM_old[1], ctl->L, ctl->Lover2);
-        unsigned long long bits = (unsigned long long)__double_as_longlong(apj_d2(ddx, ddy));   // >= 0: bit patterns order like the values
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const unsigned long long b = __shfl_xor_sync(__activemask(), bits, o); bits = b > bits ? b : bits; }
-        if ((threadIdx.x & 31) == 0) atomicMax(const_cast<unsigned long long*>(&ctl->mark_d2), bits);
+        bits = (unsigned long long)__double_as_longlong(apj_d2(ddx, ddy));   // >= 0: bit patterns order like the values
+        st.XR[ctl->cur][g] = x;     // x_real = x   (jamming.cpp:193-196)
+        st.X0[ctl->gen][g] = x;     // x0 = x
+        st.XO[ctl->gen][g] = x;     // saveOldPositions (:203)
     }
-    st.XR[ctl->cur][g] = x;     // x_real = x   (jamming.cpp:193-196)
-    st.X0[ctl->gen][g] = x;     // x0 = x
-    st.XO[ctl->gen][g] = x;     // saveOldPositions (:203)
+    // one atomic per warp (a warp that straddles two replicas -- N not a multiple of 32 -- lets every lane speak for itself)
+    const bool uniform = __match_any_sync(0xffffffffu, sys) == 0xffffffffu;
+    if (uniform) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long b = __shfl_xor_sync(0xffffffffu, bits, o); bits = b > bits ? b : bits; }
+        if ((threadIdx.x & 31) != 0) bits = 0ull;
+    }
+    if (bits) atomicMax(const_cast<unsigned long long*>(&st.ctl[sys].mark_d2), bits);
 }
 
 extern "C" int apj_mark_origin(apj_engine* e) {
