@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(OB) apj_spatial_kernel(const DevState st, cons
     const bool clip = st.slab && st.nranks > 1;                  // own columns only, no wrap in x
     const double L = ctl->L, Lh = ctl->Lover2;
     const double rmax = fmax(nc * dr_c, np * dr_p);
-    int reach = (int)floor(rmax / ctl->lp) + 1;
+    int reach = (int)floor((rmax + st.skin) / ctl->lp) + 1;   // cells are those of the last rebuild: particles may have moved by up to the skin since
     const int span = (2 * reach + 1 >= b) ? b : 2 * reach + 1;   // distinct columns / rows to visit
     const double2* __restrict__ P = st.XY[ctl->cur];
     const double2* __restrict__ CSv = st.CS[ctl->cur];
@@ -228,14 +228,16 @@ __global__ void __launch_bounds__(OB) apj_spatial_ext_kernel(const DevState st, 
     const int b = ctl->b;
     const double L = ctl->L, Lh = ctl->Lover2, lp = ctl->lp;
     const double rmax = fmax(nc * 2.0, np * 0.1);
-    const int reach = (int)floor(rmax / lp) + 1;
+    const int reach = (int)floor((rmax + st.skin) / lp) + 1;
     const int span = (2 * reach + 1 >= b) ? b : 2 * reach + 1;
     const double x_edge = -Lh + (double)(ctl->col0 + ctl->ncols) * lp;     // right edge of the slab
     const int i = blockIdx.x * OB + threadIdx.x;
     if (i < ctl->n_own) {
         const long long g = (long long)ctl->p0 + i;
         const double2 me = st.XY[ctl->cur][g];
-        if (x_edge - me.x < rmax + lp) {                                    // near enough to the edge to reach across it
+        // near enough to the edge to reach across it (minimum image: an owned particle that drifted over the periodic seam
+        // since the last rebuild has been wrapped to the other side of the box)
+        if (apj_wrap1(x_edge - me.x, L, Lh) < rmax + lp) {
             const double2 mcs = st.CS[ctl->cur][g];
             const double2 vi = st.V[ctl->gen][g];
             const double spi = sqrt(vi.x * vi.x + vi.y * vi.y);
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(OB) apj_export_edge_kernel(const DevState st, 
     for (int i = blockIdx.x * OB + threadIdx.x; i < ctl->n_own; i += gridDim.x * OB) {
         const long long g = (long long)ctl->p0 + i;
         const double2 p = st.XY[ctl->cur][g];
-        if (p.x - x_left < width) {
+        if (apj_wrap1(p.x - x_left, ctl->L, ctl->Lover2) < width) {   // minimum image: drifted over the periodic seam -> wrapped
             const int k = atomicAdd(count, 1);
             if (k < cap) {
                 const double2 cs = st.CS[ctl->cur][g], v = st.V[ctl->gen][g];

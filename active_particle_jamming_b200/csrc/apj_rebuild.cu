@@ -520,6 +520,9 @@ __global__ void __launch_bounds__(RB_BLOCK) apj_fill_tiles_kernel(const DevState
 // them in class-major order at their final position in the block's [quad][thread] list array. (Round 1 walked the
 // candidates twice with the placement inside a divergent branch: 333 warp-instructions per particle at 14 active
 // lanes, 6.5 ms at N = 16M; see profiles/r02_a_apj_verlet_build_kernel_ncu_full.txt.)
+#ifndef APJ_BUILD_BLOCKS
+#define APJ_BUILD_BLOCKS 5   // 48 registers, no spills: 5 blocks per SM when the staging array leaves room (S <= 48)
+#endif
 template <bool WRAP>
 __device__ __forceinline__ void build_lists(const DevState& st, SysCtl* __restrict__ ctl, const TileDesc& sd, const long long bg,
                                             const double2* __restrict__ sXY, unsigned short* __restrict__ stage, const int lgG) {
@@ -602,7 +605,7 @@ __device__ __forceinline__ void build_lists(const DevState& st, SysCtl* __restri
     if (total > ctl->list_max) atomicMax(&ctl->list_max, total);
 }
 
-__global__ void __launch_bounds__(APJ_TB_MAX) apj_verlet_build_kernel(const DevState st, const int lgG) {
+__global__ void __launch_bounds__(APJ_TB_MAX, APJ_BUILD_BLOCKS) apj_verlet_build_kernel(const DevState st, const int lgG) {
     const int sys = blockIdx.x / st.maxblk;
     const int blk = blockIdx.x - sys * st.maxblk;
     SysCtl* __restrict__ ctl = st.ctl + sys;

@@ -305,7 +305,9 @@ class _SlabFront:
         every rank hands the particles near its left edge to its left neighbour, counts its own pairs and the pairs
         that cross its right edge, and the shares are added."""
         nc = int(np.ceil(cutoff / 2.0))
-        edges = self._exchange_edges(cutoff)            # per local rank: edge set of the rank to its right
+        # per local rank: edge set of the rank to its right. Ownership only changes at a rebuild, so an owned particle may
+        # sit up to the skin (1.4) beyond its slab's edge: the edge zone is that much wider than the cutoff
+        edges = self._exchange_edges(cutoff + 2.0)
         shares = self._each_indexed(lambda k, r: r.spatial_correlations_share(cutoff, edges[k]))
         tot = self._allsum(np.sum(shares, axis=0))
         return dict(counts=tot[None, :nc], ori_sum=tot[None, nc:2 * nc], vel_sum=tot[None, 2 * nc:3 * nc], pair_sum=tot[None, 3 * nc:])

@@ -296,7 +296,7 @@ def main():
     if slab:
         from active_particle_jamming_b200.slab import DistSlab
         R, L, x, y, phi = synthetic_state(n_tot, rho, 12345)               # every rank draws the same box, keeps its slab
-        e = DistSlab(n_tot, L, device=local, seed=12345, max_neighbors=64)
+        e = DistSlab(n_tot, L, device=local, seed=12345)
         me = e.local[0]
         e.upload(x=x, y=y, R=R, phi=phi)
         del R, x, y, phi
@@ -316,7 +316,7 @@ def main():
             Ls = [p[1] for p in parts]
             R, x, y, phi = (np.concatenate([p[k] for p in parts]) for k in (0, 2, 3, 4))
         host = {k: pinned(v) for k, v in dict(x=x, y=y, R=R, phi=phi).items()}
-        e = DeviceEngine(n_loc, Ls, n_systems=reps, device=local, seed=12345 if reps == 1 else 12345 + rank, max_neighbors=64)
+        e = DeviceEngine(n_loc, Ls, n_systems=reps, device=local, seed=12345 if reps == 1 else 12345 + rank)
         me = e
         e.upload(**host)
     e.skip_self_term_once()

@@ -266,7 +266,9 @@ int apj_slab_get_pairs(apj_engine* e, int32_t* pairs, int64_t cap_pairs, int64_t
  * particles are its own; a pair that crosses a slab edge is counted by the rank of its LEFT particle, which needs the
  * neighbour's particles within the cutoff of the shared edge:
  *   apj_slab_export_edge           the owned particles within `width` of this slab's LEFT edge: 6 planes x | y | cos |
- *                                  sin | vx | vy of *n values (call with cap = 0 to size the buffer);
+ *                                  sin | vx | vy of *n values (call with cap = 0 to size the buffer). Ownership only changes
+ *                                  at a rebuild: use width = cutoff + skin (1.4) or more, so that partners which drifted
+ *                                  over the edge since the last rebuild are covered;
  *   apj_slab_spatial_correlations  this rank's additive share of the raw sums, given the edge set of the rank to its right
  *                                  sorted by cell row, ext_row[b+1] = first particle of each row (b = cells per side).
  * The host ships the edge sets between ranks (slab.py: torch.distributed plumbing, 10 x per run in the reference's

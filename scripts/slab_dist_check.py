@@ -53,6 +53,21 @@ def main():
     pairs = box.pair_set()
     order = box.order_orientation()[0][0]
     msd = box.msd()[0]
+    chk = box.checksum()
+    corr = box.spatial_correlations(20.0)                 # edge sets travel between the ranks (NCCL p2p), pairs across edges counted once
+    # per-rank checkpoint files, restored into a fresh set of handles
+    import tempfile
+    prefix = os.path.join(tempfile.gettempdir(), "apj_slab_ckpt_%d" % os.getppid())
+    box.save_checkpoint(prefix)
+    box2 = DistSlab(N, L, device=local, seed=1, max_neighbors=64, lanes_per_particle=1)
+    box2.load_checkpoint(prefix)
+    chk2 = box2.checksum()
+    step2 = box2.counters()["step"]
+    box2.close()
+    try:
+        os.remove("%s.rank%dof%d" % (prefix, rank, world))
+    except OSError:
+        pass
     if rank == 0:
         want = ref.download(["x", "y", "cosp", "sinp", "x_real", "y_real", "x_old", "y_old"])
         same = {k: bool(np.array_equal(got[k], want[k])) for k in want}
@@ -61,8 +76,14 @@ def main():
                   "bit_identical": same, "resetCounter": [cb["resetCounter"], cr["resetCounter"]], "step": [cb["step"], cr["step"]],
                   "pairs_equal": bool(np.array_equal(pairs, ref.pair_set())), "n_pairs": int(len(pairs)),
                   "order": [order, float(ref.order_orientation()[0][0])], "msd": [float(msd), float(ref.msd()[0])]}
+        rc = ref.spatial_correlations(20.0)
+        report["checksum"] = ["%016x" % chk, "%016x" % ref.checksum(), "%016x" % chk2]
+        report["corr_counts_equal"] = bool(np.array_equal(corr["counts"], rc["counts"]))
+        report["corr_sums_rel_err"] = float(max(np.max(np.abs(corr[k] - rc[k]) / np.maximum(np.abs(rc[k]), 1.0)) for k in ("ori_sum", "vel_sum", "pair_sum")))
+        report["checkpoint_step"] = [int(step2), int(cb["step"])]
         ok = all(same.values()) and cb["resetCounter"] == cr["resetCounter"] and report["pairs_equal"] and sum(own) == N \
-            and abs(report["order"][0] - report["order"][1]) <= 1e-12
+            and abs(report["order"][0] - report["order"][1]) <= 1e-12 and chk == ref.checksum() == chk2 and report["corr_counts_equal"] \
+            and report["corr_sums_rel_err"] <= 1e-10 and step2 == cb["step"]
         report["ok"] = bool(ok)
         print(json.dumps(report))
         ref.close()

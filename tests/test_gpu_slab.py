@@ -144,6 +144,14 @@ def test_slab_spatial_correlations_match_periodic(nranks, cutoff):
         assert np.array_equal(got["counts"], want["counts"])
         for f in ("ori_sum", "vel_sum", "pair_sum"):
             assert rel_err(got[f], want[f], floor=1.0) <= 1e-10, f
+        # ... and in the middle of a run: particles have drifted (some over a slab edge, still owned by the old rank), the
+        # cells are those of the last rebuild
+        with device_from_state(s, seed=3, lanes_per_particle=1, max_neighbors=64) as e:
+            e.step(57); box.step(57)
+            want, got = e.spatial_correlations(cutoff), box.spatial_correlations(cutoff)
+        assert np.array_equal(got["counts"], want["counts"])
+        for f in ("ori_sum", "vel_sum", "pair_sum"):
+            assert rel_err(got[f], want[f], floor=1.0) <= 1e-10, f
         from active_particle_jamming_b200 import ApjError
         with pytest.raises(ApjError):
             box.spatial_correlations(400.0)                     # slabs narrower than the cutoff: refused, not miscounted
