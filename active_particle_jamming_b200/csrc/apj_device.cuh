@@ -262,6 +262,9 @@ __device__ __forceinline__ double apj_u32_to_randuni(unsigned u) {
 // build-distance class of a list entry (apj_verlet_build_kernel): a pure function of d2, so the list order does
 // not depend on the decomposition
 __device__ __forceinline__ int apj_entry_class(double d2, double rn2, double cls_inv) {
+#ifdef APJ_NO_CLASSES   // experiment: pure slot order (more lanes of a warp on the same slot), no shortened sweeps
+    return 0;
+#endif
     return min(max((int)((d2 - rn2) * cls_inv), 0), APJ_CLASSES - 1);
 }
 // last distance class a step must sweep when the skin-test value is D (APJ_CLASSES-1 = full list): an entry of

@@ -579,8 +579,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         const unsigned long long ep = ctl->seq[0];
         if (lane < st.nranks) {
             SlabMail* m = apj_peer(st, lane, st.mail);
-            m->part[ep & 1][st.rank] = a;
-            __threadfence_system();
+            m->part[ep & 1][st.rank] = a;                              // same lane: the release store below orders it
             apj_st_release_sys(&m->flag[0][st.rank], ep + 1);
         }
         return;
@@ -982,8 +981,7 @@ __global__ void __launch_bounds__(RC_TB) apj_reduce_commit_kernel(const DevState
         const unsigned long long ep = ctl->seq[0];
         if (lane < st.nranks) {
             SlabMail* m = apj_peer(st, lane, st.mail);
-            m->part[ep & 1][st.rank] = a;
-            __threadfence_system();
+            m->part[ep & 1][st.rank] = a;                              // same lane: the release store below orders it
             apj_st_release_sys(&m->flag[0][st.rank], ep + 1);
         }
         __syncwarp();
