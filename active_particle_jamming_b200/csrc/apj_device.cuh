@@ -27,7 +27,10 @@
 #define APJ_PI 3.14159265
 #define APJ_PI2 6.28318531
 
-#define APJ_TB_MAX 256      // largest thread block of the step kernel (particles per block = tb / G)
+#ifndef APJ_TB_G1
+#define APJ_TB_G1 256       // threads per work block for one lane per particle (512: experiment)
+#endif
+#define APJ_TB_MAX (APJ_TB_G1 > 256 ? APJ_TB_G1 : 256)   // largest thread block of the step kernel (particles per block = tb / G)
 #define APJ_MAX_PIECES 6
 #define APJ_MAX_RANKS 8     // slab mode: GPUs of one box
 // Skin-aware sweep length. A list entry whose distance AT BUILD TIME was d_b can only come within

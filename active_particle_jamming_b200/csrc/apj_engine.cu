@@ -312,9 +312,6 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     // 131 072: .0221 / .0209 / .0287; 262 144: .0359 / .0432 / .0569; 524 288: .0470 / .0648 / .0992
     if (st.G == 0) st.G = st.ntot < 40000 ? 4 : (st.ntot < 200000 ? 2 : 1);
     if (st.G != 1 && st.G != 2 && st.G != 4 && st.G != 8) { e->err = "apj_create: lanes_per_particle must be 1, 2, 4 or 8"; return bail(APJ_E_INVALID); }
-#ifndef APJ_TB_G1
-#define APJ_TB_G1 256
-#endif
     st.tb = st.G == 1 ? APJ_TB_G1 : 128;
     st.ppb = st.tb / st.G;
     set_list_capacity(st, st.S);

@@ -605,7 +605,7 @@ __device__ __forceinline__ void build_lists(const DevState& st, SysCtl* __restri
     if (total > ctl->list_max) atomicMax(&ctl->list_max, total);
 }
 
-__global__ void __launch_bounds__(APJ_TB_MAX, APJ_BUILD_BLOCKS) apj_verlet_build_kernel(const DevState st, const int lgG) {
+__global__ void __launch_bounds__(APJ_TB_MAX, (APJ_TB_MAX > 256 ? 2 : APJ_BUILD_BLOCKS)) apj_verlet_build_kernel(const DevState st, const int lgG) {
     const int sys = blockIdx.x / st.maxblk;
     const int blk = blockIdx.x - sys * st.maxblk;
     SysCtl* __restrict__ ctl = st.ctl + sys;

@@ -235,7 +235,7 @@ __device__ __forceinline__ void apj_commit(SysCtl* __restrict__ ctl, const DevSt
 #ifndef APJ_BLOCKS_224
 #define APJ_BLOCKS_224 5   // 56 registers per thread: 35 warps per SM
 #endif
-constexpr int apj_blocks_for(int tb) { return tb == 256 ? APJ_BLOCKS_256 : (tb == 224 ? APJ_BLOCKS_224 : (tb == 192 ? APJ_BLOCKS_192 : APJ_BLOCKS_128)); }
+constexpr int apj_blocks_for(int tb) { return tb == 512 ? 2 : tb == 256 ? APJ_BLOCKS_256 : (tb == 224 ? APJ_BLOCKS_224 : (tb == 192 ? APJ_BLOCKS_192 : APJ_BLOCKS_128)); }
 template <int TB, int G, bool INJECT, bool SLAB, bool SPLIT>
 __global__ void __launch_bounds__(TB, apj_blocks_for(TB))
 apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const int always_full) {
@@ -1075,7 +1075,13 @@ void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int a
 
 }  // namespace
 
+#if APJ_TB_G1 == 512
+#define APJ_DISPATCH_512(CALL) if (st.tb == 512 && st.G == 1) { CALL(512, 1); } else
+#else
+#define APJ_DISPATCH_512(CALL)
+#endif
 #define APJ_DISPATCH(CALL)                                                   \
+    APJ_DISPATCH_512(CALL)                                                   \
     if (st.tb == 256 && st.G == 1) { CALL(256, 1); }                         \
     else if (st.tb == 192 && st.G == 1) { CALL(192, 1); }                    \
     else if (st.tb == 128 && st.G == 1) { CALL(128, 1); }                    \
