@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/apj_b200.h"
@@ -24,6 +25,10 @@ struct apj_engine {
     cudaGraphExec_t group_exec = nullptr;
     int m = 16;                 // step launches per group
     int kernels_per_group = 0;
+    // graphs of the SHORTER groups a caller keeps asking for (a driver stepping 10 at a time between two
+    // measurements, jamming.cpp:573): captured the second time the same remainder is seen
+    std::map<int, cudaGraphExec_t> part_exec;
+    std::map<int, int> part_seen, part_kernels;
     int max_nbox = 0;
     int max_b = 0;
     long long total_cols = 0;   // sum of b+1
@@ -31,6 +36,7 @@ struct apj_engine {
     long long launches = 0;
     bool have_state = false;
     std::vector<SysCtl> hctl;
+    bool ctl_clean = false;      // hctl equals the device control blocks (nothing that writes them was launched since the last copy)
     SysCtl* pin_ctl = nullptr;   // pinned bounce buffer of hctl: control-block copies never take the driver's pageable staging path
     std::vector<void*> allocs;
     double* d_noise = nullptr;
@@ -86,14 +92,24 @@ static int pull_ctl(apj_engine* e) {
     APJ_CUDA(e, cudaMemcpyAsync(e->pin_ctl, e->st.ctl, bytes, cudaMemcpyDeviceToHost, e->stream));
     APJ_CUDA(e, cudaStreamSynchronize(e->stream));
     memcpy(e->hctl.data(), e->pin_ctl, bytes);
+    e->ctl_clean = true;
     return APJ_OK;
+}
+// Read-only getters: no device round trip when nothing that writes the control blocks was launched since the
+// last copy (a driver that reads COM and counters of every replica after apj_step pays for ONE copy, the one
+// apj_step made). Slab ranks always copy: peers write their flags.
+static int read_ctl(apj_engine* e) {
+    if (e->ctl_clean && !e->st.slab) return APJ_OK;
+    return pull_ctl(e);
 }
 static int push_ctl(apj_engine* e) {
     const size_t bytes = sizeof(SysCtl) * e->hctl.size();
     if (!e->pin_ctl) APJ_CUDA(e, cudaMallocHost(&e->pin_ctl, bytes));
     memcpy(e->pin_ctl, e->hctl.data(), bytes);
+    e->ctl_clean = false;
     APJ_CUDA(e, cudaMemcpyAsync(e->st.ctl, e->pin_ctl, bytes, cudaMemcpyHostToDevice, e->stream));
     APJ_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->ctl_clean = true;
     return APJ_OK;
 }
 
@@ -102,26 +118,65 @@ __global__ void apj_add_target_kernel(SysCtl* ctl, int n_sys, long long n) {
     if (s < n_sys) ctl[s].target = ctl[s].step + n;
 }
 
-static ApjLaunch launcher(apj_engine* e, bool count) { return ApjLaunch{e->stream, count ? &e->launches : nullptr}; }
+static ApjLaunch launcher(apj_engine* e, bool count) { e->ctl_clean = false; return ApjLaunch{e->stream, count ? &e->launches : nullptr}; }
 
-static int build_group_graph(apj_engine* e) {
+static void drop_group_graphs(apj_engine* e) {
     if (e->group_exec) { cudaGraphExecDestroy(e->group_exec); e->group_exec = nullptr; }
-    if (e->cfg.flags & APJ_FLAG_NO_GRAPH) return APJ_OK;
-    if (e->st.slab && e->st.nranks > 1 && !e->slab_ready) return APJ_OK;   // peer addresses not known yet
+    for (auto& kv : e->part_exec) cudaGraphExecDestroy(kv.second);
+    e->part_exec.clear(); e->part_kernels.clear();
+}
+
+// `nsteps` speculative steps followed by the rebuild chain, as one graph
+static int capture_group(apj_engine* e, int nsteps, cudaGraphExec_t* exec, int* kernels) {
     cudaGraph_t graph = nullptr;
     long long dummy = 0;
     ApjLaunch l{e->stream, &dummy};
     APJ_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-    for (int k = 0; k < e->m; k++) apj_launch_step(e->st, l, nullptr, 0);
+    for (int k = 0; k < nsteps; k++) apj_launch_step(e->st, l, nullptr, 0);
     apj_launch_rebuild_chain(e->st, l, e->max_nbox, e->max_b);
     APJ_CUDA(e, cudaStreamEndCapture(e->stream, &graph));
-    APJ_CUDA(e, cudaGraphInstantiate(&e->group_exec, graph, 0));
+    APJ_CUDA(e, cudaGraphInstantiate(exec, graph, 0));
     APJ_CUDA(e, cudaGraphDestroy(graph));
-    e->kernels_per_group = (int)dummy;
+    *kernels = (int)dummy;
+    return APJ_OK;
+}
+
+static int build_group_graph(apj_engine* e) {
+    drop_group_graphs(e);
+    if (e->cfg.flags & APJ_FLAG_NO_GRAPH) return APJ_OK;
+    if (e->st.slab && e->st.nranks > 1 && !e->slab_ready) return APJ_OK;   // peer addresses not known yet
+    return capture_group(e, e->m, &e->group_exec, &e->kernels_per_group);
+}
+
+// a group of `rem` < m steps: direct launches the first time, a graph of its own from the second time on
+static int launch_part(apj_engine* e, int rem) {
+    e->ctl_clean = false;
+    // slab ranks launch directly: capturing and instantiating a graph in the middle of a run can wait on the device,
+    // and ranks that share ONE device (tests) would then stall the peers spinning on them
+    if (e->group_exec && rem > 0 && !(e->st.slab && e->st.nranks > 1)) {
+        auto it = e->part_exec.find(rem);
+        if (it == e->part_exec.end() && e->part_seen[rem]++ >= 1) {
+            cudaGraphExec_t x = nullptr;
+            int kn = 0;
+            if (int rc = capture_group(e, rem, &x, &kn)) return rc;
+            e->part_kernels[rem] = kn;
+            it = e->part_exec.emplace(rem, x).first;
+        }
+        if (it != e->part_exec.end()) {
+            APJ_CUDA(e, cudaGraphLaunch(it->second, e->stream));
+            e->launches += e->part_kernels[rem];
+            return APJ_OK;
+        }
+    }
+    ApjLaunch l = launcher(e, true);
+    for (int k = 0; k < rem; k++) apj_launch_step(e->st, l, nullptr, 0);
+    apj_launch_rebuild_chain(e->st, l, e->max_nbox, e->max_b);
+    APJ_CUDA(e, cudaGetLastError());
     return APJ_OK;
 }
 
 static int launch_group(apj_engine* e) {
+    e->ctl_clean = false;
     if (e->group_exec) {
         APJ_CUDA(e, cudaGraphLaunch(e->group_exec, e->stream));
         e->launches += e->kernels_per_group;
@@ -165,7 +220,6 @@ static int set_tile_cap(apj_engine* e, int need) {
     e->st.tile_cap = e->cfg.tile_slots > 0 ? std::max(e->cfg.tile_slots, need) : best_tile_cap(e->st, need);
     if (apj_configure_kernels(e->st) != 0 || apj_configure_rebuild(e->st) != 0) return fail(e, APJ_E_CUDA, "cannot reserve shared memory for the tile");
     if ((e->cfg.flags & APJ_FLAG_TINY_GRID) && e->st.persist_grid > 3) e->st.persist_grid = 3;
-    if (e->group_exec) { cudaGraphExecDestroy(e->group_exec); e->group_exec = nullptr; }
     return build_group_graph(e);
 }
 // after pull_ctl: returns 1 if a tile overflow was repaired (caller must run the chain again)
@@ -434,7 +488,7 @@ extern "C" int apj_create(const apj_config* cfg, const double* L, apj_engine** o
 extern "C" int apj_destroy(apj_engine* e) {
     if (!e) return APJ_OK;
     if (e->stream) cudaStreamSynchronize(e->stream);
-    if (e->group_exec) cudaGraphExecDestroy(e->group_exec);
+    drop_group_graphs(e);
     for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void* p : e->allocs) cudaFree(p);
     if (e->pin_ctl) cudaFreeHost(e->pin_ctl);
@@ -692,7 +746,7 @@ extern "C" int apj_set_com(apj_engine* e, int32_t s, const double* com, const do
 }
 extern "C" int apj_get_com(apj_engine* e, int32_t s, double* com, double* com0, double* com_old) {
     if (!e || s < 0 || s >= e->st.n_sys) return APJ_E_INVALID;
-    if (int rc = pull_ctl(e)) return rc;
+    if (int rc = read_ctl(e)) return rc;
     const SysCtl& c = e->hctl[s];
     if (com) { com[0] = c.COM[0]; com[1] = c.COM[1]; }
     if (com0) { com0[0] = c.COM0[0]; com0[1] = c.COM0[1]; }
@@ -734,6 +788,7 @@ extern "C" int apj_mark_origin(apj_engine* e) {
     if (int rc = pull_ctl(e)) return rc;
     for (auto& c : e->hctl) c.mark_d2 = 0ull;
     if (int rc = push_ctl(e)) return rc;
+    e->ctl_clean = false;
     apj_mark_origin_kernel<<<(unsigned)((st.ntot + 255) / 256), 256, 0, e->stream>>>(st);
     e->launches++;
     // COM = mean(x_real) in the deterministic two-level order of the step kernel
@@ -934,6 +989,7 @@ extern "C" int apj_step(apj_engine* e, int64_t n_steps) {
     if (n_steps == 0) return APJ_OK;
     if (int rc = maybe_shrink_tile_cap(e)) return rc;
     DevState& st = e->st;
+    e->ctl_clean = false;
     apj_add_target_kernel<<<(st.n_sys + 63) / 64, 64, 0, e->stream>>>(st.ctl, st.n_sys, n_steps);
     e->launches++;
     long long remaining = n_steps;
@@ -943,12 +999,8 @@ extern "C" int apj_step(apj_engine* e, int64_t n_steps) {
         const long long full = remaining / e->m, rem = remaining % e->m;
         for (long long k = 0; k < full; k++)
             if (int rc = launch_group(e)) return rc;
-        if (rem || !full) {
-            ApjLaunch l = launcher(e, true);
-            for (long long k = 0; k < rem; k++) apj_launch_step(st, l, nullptr, 0);
-            apj_launch_rebuild_chain(st, l, e->max_nbox, e->max_b);
-            APJ_CUDA(e, cudaGetLastError());
-        }
+        if (rem || !full)
+            if (int rc = launch_part(e, (int)rem)) return rc;
         if (int rc = pull_ctl(e)) return rc;
         int repaired = 0;
         if (int rc = repair_tile_overflow(e, &repaired)) return rc;
@@ -964,6 +1016,7 @@ extern "C" int apj_step_injected(apj_engine* e, const double* noise) {
     if (!e->have_state) return fail(e, APJ_E_STATE, "apj_step_injected: no state uploaded");
     DevState& st = e->st;
     APJ_CUDA(e, cudaMemcpyAsync(e->d_noise, noise, sizeof(double) * st.n_sys * st.N, cudaMemcpyHostToDevice, e->stream));
+    e->ctl_clean = false;
     apj_add_target_kernel<<<(st.n_sys + 63) / 64, 64, 0, e->stream>>>(st.ctl, st.n_sys, 1);
     e->launches++;
     ApjLaunch l = launcher(e, true);
@@ -993,7 +1046,7 @@ extern "C" int apj_force_rebuild(apj_engine* e) {
 
 extern "C" int apj_get_counters(apj_engine* e, int32_t s, int64_t* o) {
     if (!e || !o || s < 0 || s >= e->st.n_sys) return APJ_E_INVALID;
-    if (int rc = pull_ctl(e)) return rc;
+    if (int rc = read_ctl(e)) return rc;
     const SysCtl& c = e->hctl[s];
     o[0] = c.step; o[1] = c.reset_counter; o[2] = c.n_rebuilds; o[3] = c.list_max; o[4] = c.overflow;
     o[5] = e->launches; o[6] = c.n_discarded; o[7] = c.nbox;
@@ -1002,7 +1055,7 @@ extern "C" int apj_get_counters(apj_engine* e, int32_t s, int64_t* o) {
 static_assert(APJ_CLASSES == 4, "apj_get_sweep_stats reports four classes");
 extern "C" int apj_get_sweep_stats(apj_engine* e, int32_t s, double* o) {
     if (!e || !o || s < 0 || s >= e->st.n_sys) return APJ_E_INVALID;
-    if (int rc = pull_ctl(e)) return rc;
+    if (int rc = read_ctl(e)) return rc;
     const SysCtl& c = e->hctl[s];
     o[0] = (double)c.n_retried; o[1] = (e->st.truncate && c.trunc_ok) ? 1.0 : 0.0; o[2] = c.skinD; o[3] = c.kmin;
     for (int k = 0; k < APJ_CLASSES; k++) o[4 + k] = (double)c.n_class[k];
@@ -1275,6 +1328,7 @@ extern "C" int apj_time_step_kernel(apj_engine* e, int64_t n, float* mean_ms, in
     ApjLaunch l = launcher(e, true);
     // one target for the whole series (as apj_step does): only the very last step takes the
     // "store the observables' fields" path, every other launch is the steady-state kernel
+    e->ctl_clean = false;
     apj_add_target_kernel<<<(st.n_sys + 63) / 64, 64, 0, e->stream>>>(st.ctl, st.n_sys, n);
     e->launches++;
     for (int64_t k = 0; k < n; k++) {
@@ -1316,6 +1370,7 @@ extern "C" int apj_time_step_parts(apj_engine* e, int64_t n, float* out3) {
     evs.s = e->stream; evs.k = 0;
     for (auto& x : evs.v) APJ_CUDA(e, cudaEventCreate(&x));
     ApjLaunch l = launcher(e, true);
+    e->ctl_clean = false;
     apj_add_target_kernel<<<(st.n_sys + 63) / 64, 64, 0, e->stream>>>(st.ctl, st.n_sys, n);
     e->launches++;
     for (int64_t k = 0; k < n; k++) {

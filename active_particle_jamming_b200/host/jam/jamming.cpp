@@ -631,23 +631,40 @@ void Engine::finish()
     printer->print_summary(run, N, L, t, 1./dt, CFself, CTnoise, dens, duration, resetCounter, binder, orderAvg, variance);
 }
 
+// APJ_TIMING=1: wall-clock seconds of every phase of start() on stderr (where a short run spends its time).
+static void lap(const char* what)
+{
+    static const bool on = getenv("APJ_TIMING") && atoi(getenv("APJ_TIMING"));
+    static high_resolution_clock::time_point last = high_resolution_clock::now();
+    if (!on) return;
+    const high_resolution_clock::time_point now = high_resolution_clock::now();
+    fprintf(stderr, "[jam timing] %-28s %.3f s\n", what, duration_cast<duration<double>>(now - last).count());
+    last = now;
+}
+
 void Engine::start()
 {
+    lap("process start");
     setup();
     open_outputs();
+    lap("initCells + output tree");
     attach_device();
+    lap("apj_create + upload");
 
     assignCellsToGrid();
     buildVerletLists();
 
     relax();
+    lap("relax");
 
     check(apj_mark_origin(dev), "apj_mark_origin");       // x_real = x0 = x, COM0 = COM, saveOldPositions (:191-203)
     batch->touch();
     pending = 0;
 
     while (countdown != 0) tick();
+    lap("measurement loop");
     finish();
+    lap("finish");
 }
 
 // ---------------------------------------------------------------------------------------------

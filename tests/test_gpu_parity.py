@@ -73,6 +73,47 @@ def test_step_by_step_resynchronised(N, rho, lanes):
         o.close()
 
 
+@pytest.mark.parametrize("lanes", [1, 4, 8])
+@pytest.mark.parametrize("N", [100, 144, 256])               # b = 3, 3-4, 5 boxes per side (rn is the largest radius drawn): the smallest grids the reference is defined on
+def test_smallest_boxes(N, lanes):
+    """b = floor(L / 2 rn) = 3 is the smallest grid whose 3x3 neighbourhood does not alias (jamming.cpp:359; apj_create
+    refuses b < 3): one tile column wraps onto itself through the periodic seam on both sides. Step-by-step and
+    200 free-running Philox steps against the oracle."""
+    rho = 0.9
+    o, rng = relaxed_oracle(N, rho, seed=N + lanes, l_s=0.5, l_n=0.3)
+    L = o.scalars()["L"]
+    assert 3 <= o.scalars()["b"] <= (3 if N == 100 else 5)
+    e = device_from_state(o.state(), lanes_per_particle=lanes, seed=5)
+    try:
+        o.assign(); o.build()
+        assert np.array_equal(e.pair_set(), o.pair_set())
+        for k in range(8):
+            nz = rng.uniform(-PI, PI, N)
+            rebuilt = o.step(nz)
+            e.step_injected(nz)
+            if k == 0:
+                assert_state_close(e.download(), o, L, TOL, "step 0")
+            if rebuilt:
+                assert np.array_equal(e.pair_set(), o.pair_set())
+        e.close()
+        e = device_from_state(o.state(), lanes_per_particle=lanes, seed=5)
+        o.run_philox(5, 0, 1); e.step(1)
+        assert_state_close(e.download(), o, L, TOL, "philox step 1")
+        nreb = o.run_philox(5, 1, 199); e.step(199)
+        c = e.counters()
+        assert c["step"] == 200 and nreb > 0
+        d = e.download()
+        assert np.all((d["x"] >= -L / 2) & (d["x"] < L / 2) & (d["y"] >= -L / 2) & (d["y"] < L / 2))
+        o2 = OracleSim.from_arrays(d["R"], d["x"], d["y"], d["phi"], rho, L=L)   # a fresh build on the device's own state gives the oracle's pairs
+        o2.topology(); o2.assign(); o2.build()
+        e.force_rebuild()
+        assert np.array_equal(e.pair_set(), o2.pair_set())
+        o2.close()
+    finally:
+        e.close()
+        o.close()
+
+
 @pytest.mark.parametrize("flags", [0, 1])   # CUDA graph / direct launches
 def test_free_running_philox_matches_oracle(flags):
     """apj_step (Philox4x32-10 noise generated in the kernel, speculative multi-step launches with the
