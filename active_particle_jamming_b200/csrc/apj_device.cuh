@@ -145,6 +145,8 @@ struct DevState {
     int want_persist;           // APJ_FLAG_PERSIST
     int persist_grid;           // > 0: blocks of the persistent step kernel (one resident wave; one large system only)
     int persist_sms;            // SMs of the device (block b of the persistent grid sits in resident slot b / persist_sms)
+    int want_ring;              // APJ_STEP_RING=1: ring form of the step kernel (one block per SM, consumer groups around a ring of tile buffers)
+    int ring_nb, ring_grid;     // > 0: tile buffers of a ring block / blocks (one per SM); set by apj_configure_kernels
     unsigned long long seed;
     SysCtl* ctl;
     double2* XY[2];
@@ -170,6 +172,7 @@ struct DevState {
     int* chunk_sums;   // per system scan_chunks entries: scratch of the cell scan
     double4* partials;  // per work block {sum x_real, sum y_real, top1 d2, top2 d2}
     double4* gpartials; // per group of 32 work blocks
+    double4* wpartials; // ring kernel: per work block and warp (8 per block); null unless the ring kernel was asked for
     unsigned* gticket;  // per group arrival counter (zero between launches)
     int maxgrp;         // groups reserved per system
     // slab mode (n_sys == 1). Array slots [cap, cap+gcap) hold the left ghost column (global column
@@ -413,6 +416,11 @@ int apj_rebuild_chain_launches(const DevState& st);
 int apj_configure_kernels(DevState& st);   // also sets st.persist_grid
 int apj_configure_rebuild(const DevState& st);
 int apj_step_blocks_per_sm_limit(int tb);   // __launch_bounds__ of the step kernel
+// ring kernel: large periodic single system, one lane per particle, 256-thread tiles, split tail
+inline bool apj_ring_eligible(const DevState& st) { return st.want_ring && st.split_tail && st.n_sys == 1 && st.G == 1 && (st.tb == 256 || st.tb == 128) && !st.slab; }
+// tile buffers of a ring block (5 for 256-particle tiles, 8 for 128-particle tiles) if they fit the 227 KB of a block next to the
+// kernel's static shared memory, else 0 (classic kernel)
+inline int apj_ring_buffers(int tb, int tile_cap) { const int nb = tb == 256 ? 5 : 8; return (size_t)nb * (tile_cap + 1) * 48 <= (size_t)(232448 - 2560) ? nb : 0; }
 size_t apj_step_extra_smem(const DevState& st);   // dynamic shared memory of a step block beyond the tile
 int apj_max_list_capacity();
 int apj_scan_chunk_cells();

@@ -198,6 +198,7 @@ static int build_group_graph(apj_engine* e);
 // when a rebuild produced a tile larger than the capacity (nothing was committed, the system is
 // still stale) or when a smaller capacity would fit one more block per SM.
 static int blocks_per_sm(const DevState& st, int cap) {
+    if (apj_ring_eligible(st) && apj_ring_buffers(st.tb, cap) > 0) return apj_ring_buffers(st.tb, cap);   // ring kernel: tile buffers of the one block of an SM
     // dynamic + static shared memory of a step block + the 1 KB the driver reserves per resident block
     const size_t per_block = (size_t)(cap + 1) * 48 + (st.G > 1 ? (size_t)st.ppb * 32 : 0) + apj_step_extra_smem(st) + 768 + 1024;
     const int by_smem = (int)((size_t)233472 / per_block);
@@ -206,6 +207,11 @@ static int blocks_per_sm(const DevState& st, int cap) {
 static int best_tile_cap(const DevState& st, int need) {
     // slack before a denser tile forces a re-launch: 3 % + 8 slots (APJ_TILE_SLACK=0, tuning runs: none)
     static const int slack = getenv("APJ_TILE_SLACK") ? atoi(getenv("APJ_TILE_SLACK")) : 1;
+    if (apj_ring_eligible(st)) {                                      // ring kernel: the largest capacity its tile buffers allow, if the tiles fit it
+        const int nb = st.tb == 256 ? 5 : 8;
+        const int ring_cap = (int)((size_t)(232448 - 2560) / ((size_t)nb * 48)) - 1;
+        if (need <= ring_cap) return ring_cap;
+    }
     need = std::min(std::max(slack ? need + need / 32 + 8 : need, 64), 4094);
     const int target = blocks_per_sm(st, need);
     int lo = need, hi = 4094;                                         // largest cap with the same block count
@@ -367,6 +373,7 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     if (st.G == 0) st.G = st.ntot < 40000 ? 4 : (st.ntot < 200000 ? 2 : 1);
     if (st.G != 1 && st.G != 2 && st.G != 4 && st.G != 8) { e->err = "apj_create: lanes_per_particle must be 1, 2, 4 or 8"; return bail(APJ_E_INVALID); }
     st.tb = st.G == 1 ? APJ_TB_G1 : 128;
+    if (const char* te = getenv("APJ_TB")) if (st.G == 1 && (atoi(te) == 128 || atoi(te) == 192 || atoi(te) == 256)) st.tb = atoi(te);   // tuning runs
     st.ppb = st.tb / st.G;
     set_list_capacity(st, st.S);
     // Engine constants exactly as the reference derives them (jamming.cpp:57, :112-115, :611)
@@ -424,6 +431,8 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     if (cfg->flags & APJ_FLAG_FUSED_TAIL) st.split_tail = 0;
     st.want_persist = (cfg->flags & APJ_FLAG_PERSIST) ? 1 : 0;
     if (const char* pe = getenv("APJ_STEP_PIPE")) st.want_persist = atoi(pe) ? 1 : 0;   // tuning runs: force the pipelined kernel on / off
+    st.want_ring = 0;
+    if (const char* re = getenv("APJ_STEP_RING")) st.want_ring = atoi(re) ? 1 : 0;      // ring kernel (large periodic single systems)
     {   // tile capacity: three columns x (block rows + 2 halo rows), sized from the mean cell occupancy
         double ppc = 0;
         for (int s = 0; s < st.n_sys; s++) ppc = std::max(ppc, (double)st.N / ((double)e->hctl[s].b * e->hctl[s].b));
@@ -466,6 +475,8 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     A(dev_alloc(e, &st.cell_cursor, (size_t)cells));
     A(dev_alloc(e, &st.partials, (size_t)st.n_sys * st.maxblk));
     A(dev_alloc(e, &st.gpartials, (size_t)st.n_sys * st.maxgrp));
+    st.wpartials = nullptr;
+    if (st.want_ring) A(dev_alloc(e, &st.wpartials, (size_t)st.n_sys * st.maxblk * 8));
     A(dev_alloc(e, &st.gticket, (size_t)st.n_sys * st.maxgrp));
     A(dev_alloc(e, &e->d_noise, (size_t)st.n_sys * st.N));
     A(apj_obs_alloc(&e->obs, st, e->stream, e->allocs));
@@ -1074,6 +1085,7 @@ extern "C" int apj_get_tuning(apj_engine* e, int32_t* o) {
     for (auto& c : e->hctl) { tm = std::max(tm, c.tile_max); nb += c.nblk; }
     o[0] = e->st.G; o[1] = e->st.tb; o[2] = e->st.ppb; o[3] = e->st.tile_cap; o[4] = tm;
     o[5] = (int)((e->st.tile_cap + 1) * 48 + (e->st.G > 1 ? (size_t)e->st.ppb * 32 : 0)); o[6] = nb; o[7] = e->m;
+    if (e->st.ring_nb > 0) o[5] *= e->st.ring_nb;          // ring kernel: all tile buffers of the one block of an SM
     return APJ_OK;
 }
 extern "C" int apj_set_reset_counter(apj_engine* e, int32_t s, int64_t v) {

@@ -875,6 +875,253 @@ apj_step_pipe_kernel(const DevState st, const double* __restrict__ noise_by_id, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Ring form of the step (one large periodic system, one lane per particle, split tail): ONE block per SM made of
+// RING_NG = 3 groups of 256 threads around a ring of RING_NB = 5 tile buffers in shared memory (5 x 45 KB fit the
+// 227 KB of an SM at the tile sizes of a homogeneous box; denser tiles fall back to the classic kernel).
+//   * the block walks the tiles b, b + grid, b + 2 grid, ... (local numbers i = 0, 1, ...); group k sweeps the
+//     tiles i = k, k + 3, ...; tile i lives in buffer i % 5;
+//   * a buffer is refilled the moment its tile has been swept: the LAST warp of the group to finish the sweep of
+//     tile i (shared-memory arrival counter, no barrier) issues the TMA copies of tile i + 5 into the same buffer.
+//     The descriptor it needs arrived WITH tile i (a 64-byte bulk copy on the same mbarrier), so a refill is one trip
+//     to L2 / HBM and has more than a tile time to land;
+//   * what a tile needs from global memory besides the tile itself -- list length, id, the first list quad -- is
+//     requested by the same thread right after the sweep of its previous tile and arrives under the epilogue, so a warp
+//     goes from the last store of one tile straight into the sweep of the next: the head of the classic kernel
+//     (descriptor trip, then tile + lists trip, ~40 % of a block's life) is gone;
+//   * warps never wait for each other: one partial per WARP and tile (wpartials), folded in the classic kernel's
+//     order by apj_reduce_commit_kernel -- positions AND the committed COM / displacement maxima are bit-identical
+//     to the classic split-tail path;
+//   * 24 warps share the register file instead of 32: 80 registers per thread.
+template <int RING_NB>
+struct RingSmem {
+    TileDesc sd[RING_NB];            // descriptor of the tile in (or on its way into) buffer b
+    TileDesc nd[RING_NB];            // descriptor of the NEXT occupant of buffer b: lands with the tile
+    unsigned long long full[RING_NB];
+    unsigned done[RING_NB];          // warps that finished sweeping the tile in buffer b
+    int round[RING_NB];              // use number (i / 5) of the tile buffer b was last issued for: groups drift, and an mbarrier
+                                     // parity wait two phases ahead of the barrier would pass at once (stale tile) -- a warp
+                                     // first waits for "issued for MY round", then for the data
+    int kcls;
+};
+
+// whole warp: `dw` = the 16 descriptor words of a tile (lanes 0..15). Publishes the descriptor next to buffer `b` and
+// issues the TMA copies of the tile's pieces (+ the descriptor of the buffer's next occupant) on the buffer's mbarrier.
+template <int RING_NB>
+__device__ __forceinline__ void ring_issue(const DevState& st, RingSmem<RING_NB>& sm, unsigned char* smem_raw, const int b, const int round,
+                                           const int dw, const TileDesc* next_src, const int cur, const int gen,
+                                           const unsigned buf_bytes, const unsigned dCS) {
+    const int lane = threadIdx.x & 31;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last read through the generic proxy
+    if (lane < 16) reinterpret_cast<int*>(&sm.sd[b])[lane] = dw;
+    const int np = __shfl_sync(0xffffffffu, dw, 3) & 0xff;
+    const int mp = lane / 3, arr = lane - mp * 3;
+    int off = 1, my_off = 1, my_len = 0, my_start = 0;
+#pragma unroll
+    for (int q = 0; q < APJ_MAX_PIECES; q++) {
+        const int start = __shfl_sync(0xffffffffu, dw, 4 + q);
+        const int len = __shfl_sync(0xffffffffu, dw, 4 + APJ_MAX_PIECES + q);
+        if (q < np) {
+            if (q == mp) { my_off = off; my_len = len; my_start = start; }
+            off += len;
+        }
+    }
+    __syncwarp();                                                   // descriptor stores before lane 0's release
+    if (lane == 0) {
+        apj_mbar_expect_tx(&sm.full[b], (unsigned)(off - 1) * 48u + (next_src ? (unsigned)sizeof(TileDesc) : 0u));
+        __threadfence_block();
+        asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(apj_smem_addr(&sm.round[b])), "r"(round) : "memory");   // the barrier is in phase `round` now
+    }
+    __syncwarp();
+    if (mp < np && my_len > 0) {
+        const double2* src = arr == 0 ? st.XY[cur] : (arr == 1 ? st.CS[cur] : st.RR[gen]);
+        double2* dst = reinterpret_cast<double2*>(smem_raw + (size_t)b * buf_bytes + (size_t)arr * dCS);
+        apj_bulk_g2s(dst + my_off, src + my_start, (unsigned)my_len * 16u, &sm.full[b]);
+    }
+    if (lane == 31 && next_src) apj_bulk_g2s(&sm.nd[b], next_src, (unsigned)sizeof(TileDesc), &sm.full[b]);
+}
+
+template <int TB, int RING_NG, int RING_NB, bool INJECT>
+__global__ void __launch_bounds__(RING_NG * TB, 1)
+apj_step_ring_kernel(const DevState st, const double* __restrict__ noise_by_id, const int always_full) {
+    static_assert(RING_NG < RING_NB && RING_NG * TB == 768, "24 warps at 80 registers; at least one spare buffer");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(128) RingSmem<RING_NB> sm;
+    SysCtl* __restrict__ ctl = st.ctl;
+    const int nblk = ctl->nblk;
+    const long long step = ctl->step;
+    if ((int)blockIdx.x >= nblk || ctl->stale || step >= ctl->target) return;   // uniform over the grid
+    const int cur = ctl->cur, gen = ctl->gen;
+    const int stride = gridDim.x;
+    const int ntile = (nblk - (int)blockIdx.x + stride - 1) / stride;           // tiles of this block
+    const unsigned buf_bytes = (unsigned)(st.tile_cap + 1) * 48u;
+    const unsigned dCS = (unsigned)(st.tile_cap + 1) * 16u, dRR = 2u * dCS;
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < RING_NB; b++) {
+            apj_mbar_init(&sm.full[b], 1);
+            sm.done[b] = 0u;
+            sm.round[b] = -1;
+            *reinterpret_cast<double2*>(smem_raw + (size_t)b * buf_bytes) = make_double2(1e300, 1e300);   // sentinel slot 0
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        sm.kcls = apj_sweep_class(ctl, st);
+    }
+    __syncthreads();
+
+    const int gi = threadIdx.x / TB;
+    const int t = threadIdx.x - gi * TB, lane = t & 31, wid = t >> 5;
+    if (gi >= ntile) return;
+    const int kcls = sm.kcls;
+    const double L = ctl->L, Lh = ctl->Lover2;
+    const double rn2 = st.rn2;
+    int tile = blockIdx.x + gi * stride;
+
+    if (gi == 0 && wid == 0) {                                      // first fill of the ring: tiles 0 .. 4 of the block
+        int d[RING_NB];
+#pragma unroll
+        for (int k = 0; k < RING_NB; k++)
+            d[k] = (k < ntile && lane < 16) ? apj_ldg_l2keep(reinterpret_cast<const int*>(st.tiles + tile + k * stride) + lane) : 0;
+#pragma unroll
+        for (int k = 0; k < RING_NB; k++)
+            if (k < ntile) ring_issue(st, sm, smem_raw, k, 0, d[k], k + RING_NB < ntile ? st.tiles + tile + (k + RING_NB) * stride : nullptr,
+                                      cur, gen, buf_bytes, dCS);
+    }
+
+    int b = gi, rnd = 0;                                            // buffer of tile i = i % 5 and its use number i / 5
+    int g0 = __ldg(&st.tiles[tile].g0), n = __ldg(&st.tiles[tile].n);
+    const uint4* __restrict__ gq = reinterpret_cast<const uint4*>(st.list32) + (long long)tile * st.max_quads * TB + t;
+    uint4 q[QREG];
+    q[0] = __ldg(gq);
+    unsigned cntk_raw = t < n ? st.cntk[g0 + t] : 0u;
+    int id = st.ID[gen][g0 + (t < n ? t : 0)];
+
+    for (int i = gi;; i += RING_NG) {
+        const bool active = t < n;
+        const long long g = (long long)g0 + (active ? t : 0);
+        q[1] = st.max_quads > 1 ? __ldg(gq + TB) : make_uint4(0u, 0u, 0u, 0u);   // consumed a quad (~200 instructions) into the sweep
+
+        unsigned sXY = apj_smem_addr(smem_raw + (size_t)b * buf_bytes);
+        {
+            int r_;
+            do { asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(r_) : "r"(apj_smem_addr(&sm.round[b])) : "memory"); } while (r_ != rnd);
+        }
+        apj_mbar_wait(&sm.full[b], (unsigned)rnd & 1u, sXY);
+        const bool wraps = (sm.sd[b].info & APJ_INFO_WRAPS) != 0;
+        const unsigned own = (unsigned)(sm.sd[b].own_slot + (active ? t : 0)) * 16u;
+
+        // ---- neighborInteractions ----
+        PairAcc acc = {0.0, 0.0, 0.0, 0.0};
+        const double2 me = lds_f64x2(sXY + own);
+        double2 mcs, mrr;
+        {
+            const double Ri = lds_f64(sXY + dRR + own);
+            const int nent = (int)((cntk_raw >> (8 * kcls)) & 0xffu);
+            const int nw = (nent + 1) >> 1;
+            if (wraps) sweep<TB, true>(acc, nw, q, gq, me, Ri, sXY, dCS, dRR, L, Lh, rn2);
+            else sweep<TB, false>(acc, nw, q, gq, me, Ri, sXY, dCS, dRR, L, Lh, rn2);
+            mcs = lds_f64x2(sXY + dCS + own);               // own {cos,sin}, {R,1/R}: the last reads of the buffer
+            mrr = lds_f64x2(sXY + dRR + own);
+        }
+
+        // ---- hand the buffer back: the last warp of the group to get here refills it with tile i + 5 ----
+        {
+            unsigned last = 0;
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                last = (atomicAdd(&sm.done[b], 1u) == (unsigned)(TB / 32) - 1u) ? 1u : 0u;
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                if (lane == 0) sm.done[b] = 0u;
+                if (i + RING_NB < ntile) {
+                    __threadfence_block();
+                    const int dwn = lane < 16 ? reinterpret_cast<const int*>(&sm.nd[b])[lane] : 0;
+                    __syncwarp();
+                    ring_issue(st, sm, smem_raw, b, rnd + 1, dwn, i + 2 * RING_NB < ntile ? st.tiles + tile + 2 * RING_NB * stride : nullptr,
+                               cur, gen, buf_bytes, dCS);
+                }
+            }
+        }
+
+        // ---- own-particle inputs of the epilogue, then what this thread's next tile needs: all in flight under the epilogue ----
+        double2 xo = make_double2(0.0, 0.0), xr = xo;
+        if (active) {
+            asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(xo.x), "=d"(xo.y) : "l"(st.XO[gen] + g));
+            asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(xr.x), "=d"(xr.y) : "l"(st.XR[cur] + g));
+        }
+        const bool more = i + RING_NG < ntile;
+        const int tile_n = tile + RING_NG * stride;
+        const int my_id = id;
+        if (more) {
+            g0 = __ldg(&st.tiles[tile_n].g0); n = __ldg(&st.tiles[tile_n].n);
+            gq = reinterpret_cast<const uint4*>(st.list32) + (long long)tile_n * st.max_quads * TB + t;
+            q[0] = __ldg(gq);
+            cntk_raw = t < n ? st.cntk[g0 + t] : 0u;
+            id = st.ID[gen][g0 + (t < n ? t : 0)];
+        }
+
+        double sum_x = 0.0, sum_y = 0.0, top1 = 0.0, top2 = 0.0;
+        if (active) {
+            double u;                                       // randuni() of this step (jamming.cpp:667)
+            if (INJECT) {
+                u = noise_by_id[my_id];
+            } else {
+                const unsigned w = apj_philox_word0((unsigned)my_id, (unsigned)step, (unsigned)(step >> 32), 0u,
+                                                    (unsigned)st.seed, (unsigned)(st.seed >> 32));
+                u = apj_u32_to_randuni(w);
+            }
+            const double Ri = mrr.x;
+            double Fx = acc.Fx, Fy = acc.Fy, ax = acc.ax, ay = acc.ay;
+            if (!ctl->no_self_once) { ax += mcs.x; ay += mcs.y; }  // self term: Cell::update left x_new = cosp (Cell.h:102-103)
+            const double nz = ctl->CTnoise * u;
+            const bool want_phi = always_full || step + 1 == ctl->target;
+            double phi, sn, cs;
+            apj_new_orientation(ax, ay, nz, want_phi, phi, cs, sn);
+            double CF = ctl->CFself;
+            if (ctl->ramp_len > 0) {                        // relax() ramp (jamming.cpp:518)
+                const long long t_ = step - ctl->ramp_t0;
+                if (t_ < ctl->ramp_len) CF = CF - (double)(ctl->ramp_len - t_) * CF / (double)ctl->ramp_len;
+            }
+            Fx += cs * CF * Ri;
+            Fy += sn * CF * Ri;
+            const double vx = Fx * mrr.y, vy = Fy * mrr.y;  // Rinv = 1/R stored at upload (jamming.cpp:298)
+            const double dx = vx * st.dt, dy = vy * st.dt;
+            double x = me.x + dx, y = me.y + dy;
+            if (x >= Lh) x -= L; else if (x < -Lh) x += L;  // Cell::PBC, single wrap (Cell.h:168-175)
+            if (y >= Lh) y -= L; else if (y < -Lh) y += L;
+            st.XY[cur ^ 1][g] = make_double2(x, y);
+            st.CS[cur ^ 1][g] = make_double2(cs, sn);
+            {   // newSkinList: displacement since the last rebuild, COM drift removed (of the state the step STARTED from)
+                const double ddx = apj_delta_norm(((me.x - xo.x) - ctl->COM[0]) + ctl->COM_old[0], L, Lh);
+                const double ddy = apj_delta_norm(((me.y - xo.y) - ctl->COM[1]) + ctl->COM_old[1], L, Lh);
+                top1 = apj_d2(ddx, ddy);
+            }
+            const double xrn = xr.x + dx, yrn = xr.y + dy;
+            st.XR[cur ^ 1][g] = make_double2(xrn, yrn);
+            if (want_phi) {                                 // fields only observables read
+                st.V[gen][g] = make_double2(vx, vy);
+                st.PHI[gen][g] = phi;
+            }
+            sum_x = xrn; sum_y = yrn;
+        }
+
+        // ---- this warp's partial of the tile (apj_reduce_commit_kernel folds the 8 of a tile in warp order) ----
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum_x += __shfl_xor_sync(0xffffffffu, sum_x, o);
+            sum_y += __shfl_xor_sync(0xffffffffu, sum_y, o);
+        }
+        apj_warp_top2(top1, top1, top2);
+        if (lane == 0) st.wpartials[(long long)tile * (TB / 32) + wid] = make_double4(sum_x, sum_y, top1, top2);
+        if (!more) break;
+        tile = tile_n;
+        b += RING_NG;
+        if (b >= RING_NB) { b -= RING_NB; rnd++; }
+    }
+}
+
 // one warp: wait for the partials of all ranks, fold them in rank order, take the decision
 __device__ __forceinline__ void apj_slab_commit_warp(const DevState& st, SysCtl* __restrict__ ctl) {
     const int lane = threadIdx.x & 31;
@@ -947,7 +1194,19 @@ __global__ void __launch_bounds__(RC_TB) apj_reduce_commit_kernel(const DevState
     for (int u = 0; u < RC_PER; u++) {
         const int k = c * RC_CHUNK + t * RC_PER + u;
         if (k < nblk) {
-            const double4 b = rc_load(part + k);
+            double4 b;
+            if (st.ring_nb > 0) {            // ring kernel: one partial per warp, folded here in the classic block's order (warp 0, then 1 .. 7)
+                const int nwp = st.tb >> 5;
+                const double4* wp = st.wpartials + (long long)k * nwp;
+                b = rc_load(wp);
+                for (int w = 1; w < nwp; w++) {
+                    const double4 r = rc_load(wp + w);
+                    b.x += r.x; b.y += r.y;
+                    apj_top2_merge(b.z, b.w, r.z, r.w);
+                }
+            } else {
+                b = rc_load(part + k);
+            }
             a.x += b.x; a.y += b.y;
             apj_top2_merge(a.z, a.w, b.z, b.w);
         }
@@ -1030,6 +1289,19 @@ int configure(DevState& st) {
             st.persist_grid = sms * nb;
             st.persist_sms = sms;
         }
+        st.ring_nb = 0;
+        if ((TB == 256 || TB == 128) && apj_ring_eligible(st)) {   // ring kernel: one block per SM around nb tile buffers
+            const int nb = apj_ring_buffers(st.tb, st.tile_cap);
+            if (nb > 0) {
+                if (TB == 256 && (!set(apj_step_ring_kernel<256, 3, 5, true>, 0) || !set(apj_step_ring_kernel<256, 3, 5, false>, 0))) return -1;
+                if (TB == 128 && (!set(apj_step_ring_kernel<128, 6, 8, true>, 0) || !set(apj_step_ring_kernel<128, 6, 8, false>, 0))) return -1;
+                int dev = 0, sms = 0;
+                if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+                st.ring_nb = nb;
+                st.ring_grid = sms;
+                st.persist_grid = 0;                              // (apj_reduce_commit_kernel folds one partial per TILE)
+            }
+        }
     }
     return 0;
 }
@@ -1059,10 +1331,22 @@ void launch_pipe(const DevState& st, cudaStream_t s, const double* noise_by_id, 
     }
 }
 
+inline void launch_ring(const DevState& st, cudaStream_t s, const double* noise_by_id, int always_full) {
+    const size_t smem = (size_t)st.ring_nb * (st.tile_cap + 1) * 48;
+    if (st.tb == 256) {
+        if (noise_by_id) apj_step_ring_kernel<256, 3, 5, true><<<st.ring_grid, 768, smem, s>>>(st, noise_by_id, always_full);
+        else apj_step_ring_kernel<256, 3, 5, false><<<st.ring_grid, 768, smem, s>>>(st, nullptr, always_full);
+    } else {
+        if (noise_by_id) apj_step_ring_kernel<128, 6, 8, true><<<st.ring_grid, 768, smem, s>>>(st, noise_by_id, always_full);
+        else apj_step_ring_kernel<128, 6, 8, false><<<st.ring_grid, 768, smem, s>>>(st, nullptr, always_full);
+    }
+}
+
 template <int TB, int G>
 void launch(const DevState& st, cudaStream_t s, const double* noise_by_id, int always_full) {
     if (G == 1 && st.split_tail) {
-        if (st.persist_grid > 0) { launch_pipe<TB>(st, s, noise_by_id, always_full); apj_check_launch("apj_step_pipe_kernel"); }
+        if (st.ring_nb > 0) { launch_ring(st, s, noise_by_id, always_full); apj_check_launch("apj_step_ring_kernel"); }
+        else if (st.persist_grid > 0) { launch_pipe<TB>(st, s, noise_by_id, always_full); apj_check_launch("apj_step_pipe_kernel"); }
         else { launch_variant<TB, 1, true>(st, s, noise_by_id, always_full); apj_check_launch("apj_step_kernel (split tail)"); }
         apj_reduce_commit_kernel<<<dim3((st.maxblk + RC_CHUNK - 1) / RC_CHUNK, st.n_sys), RC_TB, 0, s>>>(st);
         apj_check_launch("apj_reduce_commit_kernel");
@@ -1104,7 +1388,8 @@ int apj_configure_kernels(DevState& st) {
 template <int TB, int G>
 static void launch_parts(const DevState& st, cudaStream_t s, void (*between)(int, void*), void* arg) {
     if (G == 1 && st.split_tail) {
-        if (st.persist_grid > 0) launch_pipe<TB>(st, s, nullptr, 0);
+        if (st.ring_nb > 0) launch_ring(st, s, nullptr, 0);
+        else if (st.persist_grid > 0) launch_pipe<TB>(st, s, nullptr, 0);
         else launch_variant<TB, 1, true>(st, s, nullptr, 0);
         between(0, arg);
         apj_reduce_commit_kernel<<<dim3((st.maxblk + RC_CHUNK - 1) / RC_CHUNK, st.n_sys), RC_TB, 0, s>>>(st);

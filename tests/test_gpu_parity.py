@@ -566,6 +566,36 @@ def test_split_tail_equals_fused_tail():
     assert np.array_equal(np.asarray(ma["COM"]), np.asarray(mc["COM"]))   # graph / direct launches: same bits
 
 
+@pytest.mark.parametrize("tb", [256, 128])
+def test_ring_step_kernel_is_bit_identical_to_the_classic_one(monkeypatch, tb):
+    """APJ_STEP_RING=1 (experimental): one block per SM, consumer groups around a ring of tile buffers
+    refilled by the last warp to finish a sweep, one partial per warp folded in the classic order. Same bits as the
+    classic split-tail path -- positions, COM, rebuild steps -- over ~8 tiles per block with refills and rebuilds."""
+    from active_particle_jamming_b200 import DeviceEngine
+    N, rho, seed = 300000, 0.9, 11
+    L = DeviceEngine.lattice_box_length(N, rho, seed)[0]
+    out = []
+    for ring in (0, 1):
+        monkeypatch.setenv("APJ_STEP_RING", str(ring))
+        monkeypatch.setenv("APJ_TB", str(tb))
+        with DeviceEngine(N, L, seed=3, lanes_per_particle=1, flags=2) as e:    # 2: split tail
+            e.init_lattice(seed)
+            e.set_activity(0.0, 0.5); e.step(120)                                # passive relaxation off the lattice
+            e.set_activity(0.1, 0.3); e.step(1)
+            tun = e.tuning()
+            e.step(170)
+            tun["smem_bytes"] = min(tun["smem_bytes"], e.tuning()["smem_bytes"])  # (a denser tile would send the handle back to the classic kernel)
+            out.append((e.download(), e.counters(), e.get_com(0), tun))
+    (a, ca, ma, ta), (b, cb, mb, tb_) = out
+    assert ta["tb"] == tb_["tb"] == tb
+    assert tb_["smem_bytes"] > 200000 > ta["smem_bytes"] > 0                     # the ring kernel was in use: 5 / 8 tile buffers fill the SM
+    assert ca["step"] == cb["step"] == 291 and ca["resetCounter"] == cb["resetCounter"] and ca["resetCounter"] >= 2
+    for f in a:
+        assert np.array_equal(a[f], b[f]), f
+    for k in ("COM", "COM0", "COM_old"):
+        assert np.array_equal(np.asarray(ma[k]), np.asarray(mb[k])), k
+
+
 def test_checkpoint_restart_continues_the_run(tmp_path):
     """apj_save_checkpoint / apj_load_checkpoint (an addition; the reference cannot resume): the restored
     handle holds the stored bits, continues the Philox stream at the stored step, takes its first step within
