@@ -33,6 +33,11 @@ namespace {
 
 struct PairAcc { double Fx, Fy, ax, ay; };
 
+// Message passing between blocks (partial -> ticket atomic -> reader): an acquire-release fence at GPU scope is what the
+// pattern needs; __threadfence() is fence.sc.gpu, whose sequentially consistent form (MEMBAR.SC + ERRBAR) sits ~1 us on
+// the critical path of a 10 us step of a small system.
+__device__ __forceinline__ void apj_fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 // shared-state-space loads by 32-bit address (keeps the sweep free of generic->shared address
 // arithmetic; the addresses derive from a register the mbarrier wait "produces", so the compiler
 // cannot hoist them above the wait)
@@ -515,12 +520,12 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
     if (lane == 0) {
         st.partials[bg] = make_double4(sum_x, sum_y, top1, top2);
         // only blocks that stored into a neighbour's ghost slots need the (expensive) system-scope fence
-        if (SLAB && (sd.info & (APJ_INFO_PUSH_LEFT | APJ_INFO_PUSH_RIGHT))) __threadfence_system(); else __threadfence();
+        if (SLAB && (sd.info & (APJ_INFO_PUSH_LEFT | APJ_INFO_PUSH_RIGHT))) __threadfence_system(); else apj_fence_gpu();
         last = (atomicAdd(gticket + grp, 1u) == (unsigned)gsize - 1u) ? 1u : 0u;
     }
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
-    __threadfence();
+    apj_fence_gpu();
     double4 a = make_double4(0.0, 0.0, 0.0, 0.0);
     if (lane < gsize) {
         const double4* q = st.partials + (long long)sys * st.maxblk + (grp << 5) + lane;
@@ -535,18 +540,28 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         const double b1 = __shfl_xor_sync(0xffffffffu, a.z, o), b2 = __shfl_xor_sync(0xffffffffu, a.w, o);
         apj_top2_merge(a.z, a.w, b1, b2);
     }
+    if (!SLAB && ngrp == 1) {
+        // a system of <= 32 work blocks (N = 1024 .. 8192: the reference's own sizes, the replicas of a sweep) has ONE group:
+        // its fold IS the system's -- folding the single group partial again adds zeros and merges (0, 0), the same bits --
+        // so the second ticket, fence and round trip (~1.5 us of a ~10 us step) are skipped
+        if (lane == 0) {
+            gticket[grp] = 0u;
+            apj_commit(ctl, st, a, kcls);
+        }
+        return;
+    }
     last = 0;
     if (lane == 0) {
         gticket[grp] = 0u;
         gpart[grp] = a;
-        if (SLAB) __threadfence_system(); else __threadfence();
+        if (SLAB) __threadfence_system(); else apj_fence_gpu();
         last = (atomicAdd(&ctl->ticket, 1u) == (unsigned)ngrp - 1u) ? 1u : 0u;
     }
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
 
     // ---- last group of this system: fold the group partials, then commit ----
-    __threadfence();
+    apj_fence_gpu();
     a = make_double4(0.0, 0.0, 0.0, 0.0);
     for (int k0 = 0; k0 < ngrp; k0 += 32 * 8) {
         double2 v01[8], v23[8];
@@ -1214,12 +1229,12 @@ __global__ void __launch_bounds__(RC_TB) apj_reduce_commit_kernel(const DevState
     a = rc_block_fold(a, s_w);
     if (t == 0) {
         gpart[c] = a;
-        __threadfence();
+        apj_fence_gpu();
         s_last = (atomicAdd(&ctl->ticket, 1u) == (unsigned)nchunk - 1u) ? 1u : 0u;
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
+    apj_fence_gpu();
     a = make_double4(0.0, 0.0, 0.0, 0.0);
     for (int k = t * RC_PER; k < nchunk; k += RC_TB * RC_PER) {   // nchunk <= RC_CHUNK for every supported size: one pass
 #pragma unroll
