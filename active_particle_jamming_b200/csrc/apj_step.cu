@@ -224,6 +224,38 @@ __device__ __forceinline__ void apj_commit(SysCtl* __restrict__ ctl, const DevSt
     }
 }
 
+// one warp: fold `cnt` partials {sum x, sum y, top-1, top-2} in a fixed order -- lane l takes l, l + 32, ..., eight
+// independent loads in flight, then a shuffle tree. Every lane returns the total.
+__device__ __forceinline__ double4 apj_fold_partials(const double4* __restrict__ src, const int cnt) {
+    const int lane = threadIdx.x & 31;
+    double4 a = make_double4(0.0, 0.0, 0.0, 0.0);
+    for (int k0 = 0; k0 < cnt; k0 += 32 * 8) {
+        double2 v01[8], v23[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int k = k0 + u * 32 + lane;
+            v01[u] = make_double2(0.0, 0.0); v23[u] = make_double2(0.0, 0.0);
+            if (k < cnt) {
+                v01[u] = __ldcg(reinterpret_cast<const double2*>(src + k));
+                v23[u] = __ldcg(reinterpret_cast<const double2*>(src + k) + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a.x += v01[u].x; a.y += v01[u].y;
+            apj_top2_merge(a.z, a.w, v23[u].x, v23[u].y);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+        const double b1 = __shfl_xor_sync(0xffffffffu, a.z, o), b2 = __shfl_xor_sync(0xffffffffu, a.w, o);
+        apj_top2_merge(a.z, a.w, b1, b2);
+    }
+    return a;
+}
+
 #ifndef APJ_PF_DIST
 #define APJ_PF_DIST 0   // blocks ahead; 0 = off. Measured on B200 (N = 16M): 444 (3 per SM) cuts the kernel 6 % from a cold L2 (ncu)
                        // but costs ~1.5 % in steady state, where consecutive launches overlap -- kept as a build option
@@ -540,6 +572,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         const double b1 = __shfl_xor_sync(0xffffffffu, a.z, o), b2 = __shfl_xor_sync(0xffffffffu, a.w, o);
         apj_top2_merge(a.z, a.w, b1, b2);
     }
+#ifndef APJ_NO_GROUP_SHORTCUT
     if (!SLAB && ngrp == 1) {
         // a system of <= 32 work blocks (N = 1024 .. 8192: the reference's own sizes, the replicas of a sweep) has ONE group:
         // its fold IS the system's -- folding the single group partial again adds zeros and merges (0, 0), the same bits --
@@ -550,6 +583,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
         }
         return;
     }
+#endif
     last = 0;
     if (lane == 0) {
         gticket[grp] = 0u;
@@ -562,31 +596,7 @@ apj_step_kernel(const DevState st, const double* __restrict__ noise_by_id, const
 
     // ---- last group of this system: fold the group partials, then commit ----
     apj_fence_gpu();
-    a = make_double4(0.0, 0.0, 0.0, 0.0);
-    for (int k0 = 0; k0 < ngrp; k0 += 32 * 8) {
-        double2 v01[8], v23[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {                  // 8 independent loads in flight per lane
-            const int k = k0 + u * 32 + lane;
-            v01[u] = make_double2(0.0, 0.0); v23[u] = make_double2(0.0, 0.0);
-            if (k < ngrp) {
-                v01[u] = __ldcg(reinterpret_cast<const double2*>(gpart + k));
-                v23[u] = __ldcg(reinterpret_cast<const double2*>(gpart + k) + 1);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            a.x += v01[u].x; a.y += v01[u].y;
-            apj_top2_merge(a.z, a.w, v23[u].x, v23[u].y);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
-        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
-        const double b1 = __shfl_xor_sync(0xffffffffu, a.z, o), b2 = __shfl_xor_sync(0xffffffffu, a.w, o);
-        apj_top2_merge(a.z, a.w, b1, b2);
-    }
+    a = apj_fold_partials(gpart, ngrp);
     if (SLAB) {
         // this rank's partial goes to every rank of the box (own mailbox included); the commit kernel
         // that follows folds them in rank order, so all ranks take the same decision

@@ -7,4 +7,6 @@ b() { name=$1; shift; timeout 600 python bench.py "$@" > ${O}_${name}.json 2> ${
 b jam1k --workload jam1k --steps 100000 --warmup 200 --no-cpu --no-e2e
 b jam65k --workload jam65k --steps 10000 --warmup 200 --no-cpu --no-e2e
 b sweep512 --workload sweep512 --steps 2000 --warmup 200 --no-cpu --no-e2e
-python scripts/driver_sweep_e2e.py 1024 100000 64 > ${O}_drv_sweep.json 2>&1; cat ${O}_drv_sweep.json
+APJ_TB=192 b sweep512_tb192 --workload sweep512 --steps 2000 --warmup 200 --no-cpu --no-e2e
+APJ_TB=128 b sweep512_tb128 --workload sweep512 --steps 2000 --warmup 200 --no-cpu --no-e2e
+
