@@ -389,6 +389,7 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
 #endif
     st.seed = cfg->seed;
     e->m = cfg->steps_per_launch > 0 ? cfg->steps_per_launch : 16;
+    if (const char* me = getenv("APJ_GROUP")) if (cfg->steps_per_launch <= 0 && atoi(me) > 0) e->m = atoi(me);   // tuning runs
 
     e->hctl.assign(st.n_sys, SysCtl{});
     long long cells = 0, cols = 0;
