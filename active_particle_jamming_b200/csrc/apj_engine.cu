@@ -430,6 +430,10 @@ static int create_impl(const apj_config* cfg, const double* L, const SlabSpec& s
     st.split_tail = (st.G == 1 && (long long)st.n_sys * st.maxblk >= APJ_SPLIT_MIN_BLOCKS && st.maxblk <= 1024 * 1024) ? 1 : 0;
     if (st.G == 1 && (cfg->flags & APJ_FLAG_SPLIT_TAIL) && st.maxblk <= 1024 * 1024) st.split_tail = 1;
     if (cfg->flags & APJ_FLAG_FUSED_TAIL) st.split_tail = 0;
+    // launch-bound sizes: groups of 32 halve the share of the idle rebuild chain that ends every group (measured on one box, 16 / 32 / 64:
+    // jam1k 9.84e7 / 1.011e8 / 1.021e8, jam65k 4.80e9 / 4.90e9 / 4.89e9, sweep512 7.09e9 / 7.42e9 / 7.37e9); large systems
+    // pay for every launch that idles after a rebuild fired and stay at 16
+    if (cfg->steps_per_launch <= 0 && !getenv("APJ_GROUP") && (long long)st.n_sys * st.maxblk < APJ_SPLIT_MIN_BLOCKS) e->m = 32;
     st.want_persist = (cfg->flags & APJ_FLAG_PERSIST) ? 1 : 0;
     if (const char* pe = getenv("APJ_STEP_PIPE")) st.want_persist = atoi(pe) ? 1 : 0;   // tuning runs: force the pipelined kernel on / off
     st.want_ring = 0;

@@ -41,7 +41,7 @@ typedef struct apj_config {
     double rs_factor;      /* 0 -> 1.5  (rs = 1.5*rn, jamming.cpp:113) */
     uint64_t seed;         /* Philox4x32-10 key */
     int32_t max_neighbors; /* INITIAL capacity of one full Verlet list; 0 -> 48. Grown on demand up to 96 (periodic handles) */
-    int32_t steps_per_launch; /* speculative steps between rebuild checks; 0 -> 16 */
+    int32_t steps_per_launch; /* speculative steps between rebuild checks; 0 -> 16 (32 for systems of fewer than 4096 work blocks) */
     int32_t flags;         /* APJ_FLAG_* */
     int32_t tile_slots;    /* shared-memory tile capacity of a work block, in particles; 0 -> adaptive (follows the largest tile) */
     int32_t lanes_per_particle; /* threads cooperating on one neighbour sweep: 1, 2, 4, 8; 0 -> by system size */
